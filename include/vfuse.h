@@ -1,0 +1,201 @@
+/* vfuse.h — C ABI of libvfuse.so: the B200 (sm_100a) vision-encode-and-fuse kernels.
+ *
+ * The reference (casinca/LLM-quest) is pure Python/PyTorch and has NO FFI of its own for this path
+ * (SURVEY.md §8b); its boundary is a set of nn.Module.forward methods. Every entry point below
+ * therefore cites the reference *Python* call site whose ATen ops it replaces (paths relative to
+ * the reference root). The Python drop-in modules in llm_quest_b200/ bind these with ctypes
+ * (llm_quest_b200/_lib.py); INTEGRATION.md shows the binding a reference maintainer would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - nothing allocates, nothing synchronises: work is enqueued on `stream` (a cudaStream_t passed
+ *     as void*; NULL = legacy default stream);
+ *   - return value 0 = ok, negative = error (VF_ERR_*); vf_last_error() gives the message
+ *     (thread-local);
+ *   - bf16 = raw IEEE bfloat16 bits (uint16_t), row-major, innermost dimension contiguous;
+ *   - there is NO CPU fallback: on a machine without an sm_100 GPU every compute entry point
+ *     returns VF_ERR_NO_DEVICE / VF_ERR_CUDA.
+ */
+#ifndef VFUSE_H_
+#define VFUSE_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VF_VERSION 100 /* 0.1.0 */
+
+enum {
+  VF_OK = 0,
+  VF_ERR_ARG = -1,
+  VF_ERR_CUDA = -2,
+  VF_ERR_NO_DEVICE = -3,
+  VF_ERR_ALIGN = -4
+};
+
+int vf_version(void);
+const char* vf_last_error(void);
+/* number of kernels this library has launched since load (or since the last reset); bench.py
+ * reports it as "gpu_launches". */
+int64_t vf_launch_count(void);
+void vf_launch_count_reset(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Dense contraction: out = epilogue(A[M,K] · W[N,K]^T)  — tcgen05/TMEM GEMM, TMA-fed.
+ * A, W bf16; fp32 accumulate. Replaces every nn.Linear on the path:
+ *   qkv / proj        llm_quest/qwen/qwen3_5/qwen3_5_vision_model.py:150-151,168,190
+ *   ffn lin1 / lin2   llm_quest/qwen/qwen3_5/qwen3_5_vision_model.py:120-125
+ *   merger lin1/lin2  llm_quest/qwen/qwen3_5/qwen3_5_vision_model.py:407-409,429
+ *   Part-1 q/k/v/out  llm_quest/multimodal/vision_transformer/vit_attention.py:58-60,89
+ *   Part-1 ffn, head  llm_quest/multimodal/vision_transformer/vit_transformer_block.py:58-67,
+ *                     vit_model.py:158-159
+ *   ViTAdapter        llm_quest/multimodal/vision_transformer/vit_engine.py:44-59
+ * ------------------------------------------------------------------------------------------- */
+typedef enum {
+  VF_EPI_BIAS_BF16 = 0,      /* out_bf16 = acc + bias                                         */
+  VF_EPI_BIAS_F32 = 1,       /* out_f32  = acc + bias                                         */
+  VF_EPI_BIAS_RES_F32 = 2,   /* out_f32  = acc + bias + res_f32 (res may alias out)           */
+  VF_EPI_GELU_TANH_BF16 = 3, /* out_bf16 = gelu_tanh(acc + bias)   (vision_model.py:122)      */
+  VF_EPI_GELU_ERF_BF16 = 4,  /* out_bf16 = gelu_erf(acc + bias)    (vision_model.py:408)      */
+  VF_EPI_QKV_ROPE_BF16 = 5,  /* out_bf16 = rope2d(acc + bias) on cols < rope_cols, head=64    */
+  VF_EPI_SCATTER_BF16 = 6    /* out_bf16[dst_rows[m]] = acc + bias (early-fusion scatter)     */
+} vf_epilogue_mode;
+
+typedef struct {
+  int32_t mode;            /* vf_epilogue_mode */
+  const float* bias;       /* [N] fp32 or NULL */
+  void* out;               /* bf16 or fp32 per mode */
+  int64_t ldo;             /* out row pitch in elements */
+  const float* res;        /* [.., ldr] fp32 residual (VF_EPI_BIAS_RES_F32) */
+  int64_t ldr;
+  /* output row remap: out_row = (m / grp_rows) * grp_stride + (m % grp_rows) + row_off.
+   * grp_rows <= 0 means identity. Used to write adapter rows into a wider fused buffer
+   * (multimodal/vlm_engine.py:114 torch.cat) */
+  int32_t grp_rows;
+  int64_t grp_stride;
+  int64_t row_off;
+  /* VF_EPI_QKV_ROPE_BF16: cos/sin tables [rope_period, 32] fp32 (the first half of the reference's
+   * duplicated [n,64] tables, common/rope.py:477-480); row m uses table row m % rope_period. */
+  const float* rope_cos;
+  const float* rope_sin;
+  int32_t rope_period;
+  int32_t rope_cols;       /* columns [0, rope_cols) are rotated (q and k); multiple of 64 */
+  /* VF_EPI_SCATTER_BF16 */
+  const int32_t* dst_rows; /* [M] destination row or -1 */
+} vf_epilogue;
+
+int vf_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, int32_t M, int32_t N,
+                 int32_t K, const vf_epilogue* ep, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Patch embedding as an im2col-free GEMM: the A operand is gathered by 5-D TMA boxes straight from
+ * the pixel tensor. Replaces
+ *   nn.Conv3d(k=s=(tp,P,P)) + flatten(2).transpose(1,2) + pos-embed add
+ *       llm_quest/qwen/qwen3_5/qwen3_5_vision_model.py:79-86,105-107,353-358
+ *   nn.Conv2d(k=s=P) + flatten/transpose (+ cls/pos add done by vf_vit_cls_pos)
+ *       llm_quest/multimodal/vision_transformer/vit_model.py:48-55,77-87,145   (T = tp = 1)
+ * pixels: bf16 [B, C, T, H, W]; weight: bf16 [N, C*tp*P*P] (the conv weight flattened, K order
+ * c,dt,py,px); out: fp32, token (b, t', ph, pw) is written to row
+ *   b*out_rows_per_sample + out_row_off + (t'*nh + ph)*nw + pw,   pitch ldo elements,
+ * and gets  + bias[N] + pos[(ph*nw + pw) * ld_pos + :]  (pos may be NULL).
+ * ------------------------------------------------------------------------------------------- */
+int vf_patch_embed(const void* pixels, int32_t B, int32_t C, int32_t T, int32_t H, int32_t W,
+                   int32_t P, int32_t tp, const void* weight, const float* bias, const float* pos,
+                   int64_t ld_pos, int32_t N, float* out, int64_t ldo, int64_t out_rows_per_sample,
+                   int64_t out_row_off, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused bidirectional attention, head_dim 64, bf16 in/out, fp32 softmax (tcgen05 + TMEM).
+ * Replaces F.scaled_dot_product_attention(q,k,v) + the transposes around it
+ *   llm_quest/qwen/qwen3_5/qwen3_5_vision_model.py:169-190
+ *   llm_quest/multimodal/vision_transformer/vit_attention.py:62-87
+ * qkv: bf16 [B*S, 3*H*64] token-major, columns [q heads | k heads | v heads] (the layout
+ * nn.Linear(d, 3d) produces, vision_model.py:168-173); out: bf16 [B*S, H*64] token-major.
+ * Attention is over the S tokens of one sample; scale = softmax scale (1/sqrt(64)).
+ * ------------------------------------------------------------------------------------------- */
+int vf_attention_fwd(const void* qkv, void* out, int32_t B, int32_t S, int32_t H, float scale,
+                     void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * LayerNorm over the last dim, fp32 or bf16 in, bf16 or fp32 out, fp32 statistics.
+ *   variant 0: (x-mean)/sqrt(var+eps)*w+b   nn.LayerNorm    vision_model.py:213-214,229,234,406
+ *   variant 1: (x-mean)/(std+eps)*w+b       Part-1 LayerNorm vit_transformer_block.py:21-31
+ * merge > 1 additionally applies the 2x2 (merge x merge) spatial-merge gather of ViTMergeAdapter
+ * (vision_model.py:425-427): input token (f, r, c) of a sample with nh x nw patches per frame is
+ * written to row ((f*(nh/m) + r/m)*(nw/m) + c/m) of the sample, feature slot (r%m)*m + c%m.
+ * in_dtype / out_dtype: 0 = fp32, 1 = bf16.
+ * ------------------------------------------------------------------------------------------- */
+int vf_layernorm(const void* x, int32_t in_dtype, int64_t ldx, const float* w, const float* b,
+                 void* out, int32_t out_dtype, int64_t rows, int32_t D, float eps, int32_t variant,
+                 int32_t merge, int32_t nh, int32_t nw, void* stream);
+
+/* Part-1 class-token rows: out[b*S + 0, :] = cls[:] + pos[0, :]   (vit_model.py:86-87,145) */
+int vf_vit_cls_pos(const float* cls, const float* pos, float* out, int32_t B, int64_t rows_per_sample,
+                   int32_t D, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Rotate-half RoPE, standalone (drop-in for VisionRoPE.apply / RoPE.apply,
+ * llm_quest/common/rope.py:180-243,485-500). x: [B, H, S, hd] (dtype 0 fp32 / 1 bf16), contiguous.
+ * cos/sin: fp32 [>=S, rot] (duplicated halves as the reference builds them); position_ids: int64
+ * [B, S] or NULL (then position = s). rot <= hd; columns >= rot pass through.
+ * ------------------------------------------------------------------------------------------- */
+int vf_rope_apply(const void* x, void* out, int32_t dtype, int32_t B, int32_t H, int32_t S,
+                  int32_t hd, const float* cos, const float* sin, int32_t rot, int64_t table_rows,
+                  const int64_t* position_ids, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * MRoPE-I apply with optional fused zero-centred RMSNorm over hd.
+ * Replaces RoPE.apply_mrope + interleave_mrope_coeffs (common/rope.py:246-358) and, when
+ * norm_weight != NULL (fp32 [hd], already 1+scale), the ZeroCenteredRMSNorm before it
+ * (qwen/qwen3_next/qwen3_next_attention.py:41-46; call site qwen3_5_text_model.py:227-233).
+ * x/out: [B, H, S, hd]; cos/sin: fp32 [table_rows, rot]; position_ids: int64 [3, B, S];
+ * sections: the three mrope_section ints (T, H, W).
+ * ------------------------------------------------------------------------------------------- */
+int vf_mrope_apply(const void* x, void* out, int32_t dtype, int32_t B, int32_t H, int32_t S,
+                   int32_t hd, const float* cos, const float* sin, int32_t rot, int64_t table_rows,
+                   const int64_t* position_ids, int32_t sec_t, int32_t sec_h, int32_t sec_w,
+                   const float* norm_weight, float norm_eps, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * MRoPE 3-D position ids (bit-exact integer work). Replaces Qwen3_5VLM.compute_3d_position_ids
+ * (llm_quest/qwen/qwen3_5/qwen3_5_vlm_model.py:85-176).
+ * input_ids int64 [b, seq]; image_mask uint8/bool [b, seq] or NULL (then ids == image_token_id);
+ * feeds_host: HOST int64 [n_feeds, 3] (t, h, w) — the reference keeps it on the CPU too (:83);
+ * out int64 [3, b, seq]. n_feeds == 0 gives the text-only arange.
+ * ------------------------------------------------------------------------------------------- */
+int vf_mrope_position_ids(const int64_t* input_ids, const uint8_t* image_mask, int64_t image_token_id,
+                          const int64_t* feeds_host, int32_t n_feeds, int32_t merge, int32_t b,
+                          int32_t seq, int64_t* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Early fusion: embedding gather + masked scatter of vision rows in one pass. Replaces
+ *   emb_dict(input_ids) ... masked_scatter(image_mask, vision_embeds.to(dtype))
+ *   llm_quest/qwen/qwen3_5/qwen3_5_vlm_model.py:198-211
+ * table bf16 [vocab, D]; vision [n_vis, D] (vis_dtype 0 fp32 / 1 bf16); out bf16 [b*seq, D].
+ * The j-th placeholder in flat (b, seq) order receives vision row j. row_map (int32 [b*seq],
+ * optional) receives j for placeholder rows and -1 elsewhere; n_placeholders (int32[1], optional)
+ * the count. scratch: int32 [b*seq + 1024] workspace. If there are more placeholders than n_vis
+ * rows the extra rows are left as the table row and *n_placeholders still reports the count (the
+ * host mirror raises like masked_scatter does).
+ * vf_fuse_scan produces row_map / n_placeholders and, when inv_map != NULL, the inverse map
+ * inv_map[j] = flat token row of the j-th placeholder (-1 for j >= #placeholders; int32 [inv_cap]),
+ * which is what VF_EPI_SCATTER_BF16 consumes as dst_rows.
+ * ------------------------------------------------------------------------------------------- */
+int vf_fuse_scan(const int64_t* input_ids, const uint8_t* image_mask, int64_t image_token_id,
+                 int64_t n_tokens, int32_t* row_map, int32_t* n_placeholders, int32_t* inv_map,
+                 int64_t inv_cap, int32_t* scratch, void* stream);
+int vf_embed_gather_scatter(const int64_t* input_ids, const void* table, int64_t vocab, int32_t D,
+                            const void* vision, int32_t vis_dtype, int64_t n_vis,
+                            const int32_t* row_map, void* out, int64_t n_tokens, int32_t skip_vision,
+                            void* stream);
+
+/* dtype casts used at the module seam (fp32 pixels -> bf16, vision_model.py:210 .to(dtype)) */
+int vf_cast_f32_to_bf16(const float* x, void* out, int64_t n, void* stream);
+int vf_cast_bf16_to_f32(const void* x, float* out, int64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VFUSE_H_ */

@@ -1,0 +1,308 @@
+"""ctypes binding of libvfuse.so (include/vfuse.h) plus thin tensor-level wrappers.
+
+The library is the product; this file only marshals ``torch.Tensor`` storage pointers, shapes and
+the current CUDA stream into the C ABI. There is deliberately NO fallback: if the shared library is
+missing, or a call fails, an exception is raised (``VFuseError``) — nothing silently reverts to
+PyTorch ops.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+import torch
+
+_PKG = Path(__file__).resolve().parent
+_LIB_PATH = Path(os.environ.get("VFUSE_LIB", _PKG / "libvfuse.so"))
+
+VF_EPI_BIAS_BF16 = 0
+VF_EPI_BIAS_F32 = 1
+VF_EPI_BIAS_RES_F32 = 2
+VF_EPI_GELU_TANH_BF16 = 3
+VF_EPI_GELU_ERF_BF16 = 4
+VF_EPI_QKV_ROPE_BF16 = 5
+VF_EPI_SCATTER_BF16 = 6
+
+EXPORTS = [
+    "vf_version", "vf_last_error", "vf_launch_count", "vf_launch_count_reset", "vf_gemm_bf16",
+    "vf_patch_embed", "vf_attention_fwd", "vf_layernorm", "vf_vit_cls_pos", "vf_rope_apply",
+    "vf_mrope_apply", "vf_mrope_position_ids", "vf_fuse_scan", "vf_embed_gather_scatter",
+    "vf_cast_f32_to_bf16", "vf_cast_bf16_to_f32",
+]
+
+
+class VFuseError(RuntimeError):
+    """A libvfuse entry point returned a non-zero status (or the library is missing)."""
+
+
+class vf_epilogue(C.Structure):
+    _fields_ = [
+        ("mode", C.c_int32),
+        ("bias", C.c_void_p),
+        ("out", C.c_void_p),
+        ("ldo", C.c_int64),
+        ("res", C.c_void_p),
+        ("ldr", C.c_int64),
+        ("grp_rows", C.c_int32),
+        ("grp_stride", C.c_int64),
+        ("row_off", C.c_int64),
+        ("rope_cos", C.c_void_p),
+        ("rope_sin", C.c_void_p),
+        ("rope_period", C.c_int32),
+        ("rope_cols", C.c_int32),
+        ("dst_rows", C.c_void_p),
+    ]
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load libvfuse.so once; raise VFuseError (never fall back) when it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not _LIB_PATH.exists():
+        raise VFuseError(
+            f"{_LIB_PATH} not found: build it with `python -m llm_quest_b200.build` "
+            "(there is no PyTorch/CPU fallback for the vision-encode-and-fuse kernels)"
+        )
+    L = C.CDLL(str(_LIB_PATH))
+    vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+    L.vf_version.restype = C.c_int
+    L.vf_last_error.restype = C.c_char_p
+    L.vf_launch_count.restype = C.c_int64
+    L.vf_launch_count_reset.restype = None
+    sigs = {
+        "vf_gemm_bf16": [vp, i64, vp, i64, i32, i32, i32, C.POINTER(vf_epilogue), vp],
+        "vf_patch_embed": [vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, i64, i32, vp, i64, i64, i64, vp],
+        "vf_attention_fwd": [vp, vp, i32, i32, i32, f32, vp],
+        "vf_layernorm": [vp, i32, i64, vp, vp, vp, i32, i64, i32, f32, i32, i32, i32, i32, vp],
+        "vf_vit_cls_pos": [vp, vp, vp, i32, i64, i32, vp],
+        "vf_rope_apply": [vp, vp, i32, i32, i32, i32, i32, vp, vp, i32, i64, vp, vp],
+        "vf_mrope_apply": [vp, vp, i32, i32, i32, i32, i32, vp, vp, i32, i64, vp, i32, i32, i32, vp, f32, vp],
+        "vf_mrope_position_ids": [vp, vp, i64, vp, i32, i32, i32, i32, vp, vp],
+        "vf_fuse_scan": [vp, vp, i64, i64, vp, vp, vp, i64, vp, vp],
+        "vf_embed_gather_scatter": [vp, vp, i64, i32, vp, i32, i64, vp, vp, i64, i32, vp],
+        "vf_cast_f32_to_bf16": [vp, vp, i64, vp],
+        "vf_cast_bf16_to_f32": [vp, vp, i64, vp],
+    }
+    for name, args in sigs.items():
+        fn = getattr(L, name)
+        fn.argtypes = args
+        fn.restype = C.c_int
+    _lib = L
+    return L
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib().vf_last_error().decode(errors="replace")
+        raise VFuseError(f"{what} failed with status {rc}: {msg}")
+
+
+def launch_count() -> int:
+    return int(lib().vf_launch_count())
+
+
+def reset_launch_count() -> None:
+    lib().vf_launch_count_reset()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t) -> int | None:
+    return None if t is None else t.data_ptr()
+
+
+def _require_cuda(*ts) -> None:
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise VFuseError(
+                "libvfuse kernels need CUDA tensors (sm_100a); got a CPU tensor and there is no CPU fallback"
+            )
+
+
+_DT = {torch.float32: 0, torch.bfloat16: 1}
+
+
+# ------------------------------------------------------------------------------------------------
+# tensor-level wrappers
+# ------------------------------------------------------------------------------------------------
+def gemm(a, w, mode, out, bias=None, res=None, rope=None, dst_rows=None, grp_rows=0, grp_stride=0, row_off=0):
+    """out = epilogue(a @ w.T). a [M,K] bf16 (row stride free), w [N,K] bf16, see vf_epilogue_mode."""
+    _require_cuda(a, w, out, bias, res, dst_rows)
+    assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and a.dim() == 2 and w.dim() == 2
+    assert a.stride(1) == 1 and w.stride(1) == 1 and out.stride(-1) == 1
+    M, K = a.shape
+    N = w.shape[0]
+    assert w.shape[1] == K
+    ep = vf_epilogue()
+    ep.mode = mode
+    ep.bias = _p(bias)
+    ep.out = out.data_ptr()
+    ep.ldo = out.stride(-2) if out.dim() >= 2 else N
+    if res is not None:
+        assert res.dtype == torch.float32 and res.stride(-1) == 1
+        ep.res = res.data_ptr()
+        ep.ldr = res.stride(-2)
+    ep.grp_rows, ep.grp_stride, ep.row_off = grp_rows, grp_stride, row_off
+    if rope is not None:
+        cos_h, sin_h, period, cols = rope
+        assert cos_h.dtype == torch.float32 and cos_h.shape[-1] == 32 and cos_h.is_contiguous()
+        ep.rope_cos, ep.rope_sin, ep.rope_period, ep.rope_cols = cos_h.data_ptr(), sin_h.data_ptr(), period, cols
+    ep.dst_rows = _p(dst_rows)
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.is_contiguous() and bias.numel() == N
+    check(lib().vf_gemm_bf16(a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), M, N, K, C.byref(ep), _stream()),
+          "vf_gemm_bf16")
+    return out
+
+
+def patch_embed(pixels, weight2d, bias, pos, out, P, tp, out_rows_per_sample, out_row_off):
+    """pixels bf16 [B,C,T,H,W]; weight2d bf16 [N, C*tp*P*P]; out fp32 [rows, N] (see vfuse.h)."""
+    _require_cuda(pixels, weight2d, out)
+    assert pixels.dtype == torch.bfloat16 and pixels.is_contiguous() and pixels.dim() == 5
+    B, Cc, T, H, W = pixels.shape
+    N = weight2d.shape[0]
+    check(
+        lib().vf_patch_embed(pixels.data_ptr(), B, Cc, T, H, W, P, tp, weight2d.data_ptr(), _p(bias), _p(pos),
+                             pos.stride(0) if pos is not None else 0, N, out.data_ptr(), out.stride(-2),
+                             out_rows_per_sample, out_row_off, _stream()),
+        "vf_patch_embed",
+    )
+    return out
+
+
+def attention(qkv, out, B, S, H, scale):
+    _require_cuda(qkv, out)
+    assert qkv.dtype == torch.bfloat16 and qkv.is_contiguous() and out.dtype == torch.bfloat16 and out.is_contiguous()
+    assert qkv.numel() == B * S * 3 * H * 64 and out.numel() == B * S * H * 64
+    check(lib().vf_attention_fwd(qkv.data_ptr(), out.data_ptr(), B, S, H, float(scale), _stream()), "vf_attention_fwd")
+    return out
+
+
+def layernorm(x2d, w, b, out, eps, variant=0, merge=1, nh=0, nw=0):
+    _require_cuda(x2d, w, b, out)
+    rows, D = x2d.shape
+    assert x2d.stride(1) == 1 and out.is_contiguous()
+    check(
+        lib().vf_layernorm(x2d.data_ptr(), _DT[x2d.dtype], x2d.stride(0), w.data_ptr(), b.data_ptr(), out.data_ptr(),
+                           _DT[out.dtype], rows, D, float(eps), variant, merge, nh, nw, _stream()),
+        "vf_layernorm",
+    )
+    return out
+
+
+def vit_cls_pos(cls, pos, out, B, rows_per_sample, D):
+    _require_cuda(cls, pos, out)
+    check(lib().vf_vit_cls_pos(cls.data_ptr(), pos.data_ptr(), out.data_ptr(), B, rows_per_sample, D, _stream()),
+          "vf_vit_cls_pos")
+
+
+def rope_apply(x, cos, sin, position_ids=None):
+    _require_cuda(x, cos, sin, position_ids)
+    B, H, S, hd = x.shape
+    xc = x.contiguous()
+    out = torch.empty_like(xc)
+    pid = None if position_ids is None else position_ids.to(torch.int64).contiguous()
+    check(
+        lib().vf_rope_apply(xc.data_ptr(), out.data_ptr(), _DT[x.dtype], B, H, S, hd, cos.data_ptr(), sin.data_ptr(),
+                            cos.shape[-1], cos.shape[0], _p(pid), _stream()),
+        "vf_rope_apply",
+    )
+    return out
+
+
+def mrope_apply(x, cos, sin, position_ids, mrope_section, norm_weight=None, norm_eps=1e-6):
+    _require_cuda(x, cos, sin, position_ids, norm_weight)
+    B, H, S, hd = x.shape
+    xc = x.contiguous()
+    out = torch.empty_like(xc)
+    pid = position_ids.to(torch.int64).contiguous()
+    st, sh, sw = (int(v) for v in mrope_section)
+    check(
+        lib().vf_mrope_apply(xc.data_ptr(), out.data_ptr(), _DT[x.dtype], B, H, S, hd, cos.data_ptr(), sin.data_ptr(),
+                             cos.shape[-1], cos.shape[0], pid.data_ptr(), st, sh, sw, _p(norm_weight),
+                             float(norm_eps), _stream()),
+        "vf_mrope_apply",
+    )
+    return out
+
+
+def mrope_position_ids(input_ids, image_mask, image_token_id, feeds_cpu, merge):
+    """input_ids int64 [b, seq] (cuda); feeds_cpu: CPU int64 [F,3] or None-equivalent empty."""
+    _require_cuda(input_ids, image_mask)
+    b, seq = input_ids.shape
+    ids = input_ids.to(torch.int64).contiguous()
+    mask = None if image_mask is None else image_mask.to(torch.uint8).contiguous()
+    feeds = feeds_cpu.to(device="cpu", dtype=torch.int64).contiguous()
+    out = torch.empty((3, b, seq), dtype=torch.int64, device=input_ids.device)
+    check(
+        lib().vf_mrope_position_ids(ids.data_ptr(), _p(mask), int(image_token_id), feeds.data_ptr(), feeds.shape[0],
+                                    int(merge), b, seq, out.data_ptr(), _stream()),
+        "vf_mrope_position_ids",
+    )
+    return out
+
+
+def fuse_scan(input_ids, image_mask, image_token_id, inv_cap=0):
+    """Returns (row_map int32 [b*seq], n_placeholders int32 [1], inv_map int32 [inv_cap] or None) —
+    all on device, no sync. inv_map[j] = flat token row of the j-th placeholder, -1 beyond."""
+    _require_cuda(input_ids, image_mask)
+    ids = input_ids.to(torch.int64).contiguous()
+    n = ids.numel()
+    mask = None if image_mask is None else image_mask.to(torch.uint8).contiguous()
+    row_map = torch.empty(n, dtype=torch.int32, device=ids.device)
+    count = torch.empty(1, dtype=torch.int32, device=ids.device)
+    inv = torch.empty(inv_cap, dtype=torch.int32, device=ids.device) if inv_cap > 0 else None
+    scratch = torch.empty(n // 1024 + 1024, dtype=torch.int32, device=ids.device)
+    check(
+        lib().vf_fuse_scan(ids.data_ptr(), _p(mask), int(image_token_id), n, row_map.data_ptr(), count.data_ptr(),
+                           _p(inv), inv_cap, scratch.data_ptr(), _stream()),
+        "vf_fuse_scan",
+    )
+    return row_map, count, inv
+
+
+def embed_gather_scatter(input_ids, table, vision, row_map, out, skip_vision=False, n_vis=None):
+    _require_cuda(input_ids, table, vision, row_map, out)
+    ids = input_ids.to(torch.int64).contiguous()
+    assert table.dtype == torch.bfloat16 and table.is_contiguous() and out.dtype == torch.bfloat16 and out.is_contiguous()
+    D = table.shape[1]
+    n_vis, vd = (0 if n_vis is None else int(n_vis)), 1
+    if vision is not None:
+        assert vision.is_contiguous() and vision.shape[-1] == D
+        n_vis, vd = vision.numel() // D, _DT[vision.dtype]
+    check(
+        lib().vf_embed_gather_scatter(ids.data_ptr(), table.data_ptr(), table.shape[0], D, _p(vision), vd, n_vis,
+                                      _p(row_map), out.data_ptr(), ids.numel(), int(skip_vision), _stream()),
+        "vf_embed_gather_scatter",
+    )
+    return out
+
+
+def to_bf16(x):
+    _require_cuda(x)
+    if x.dtype == torch.bfloat16:
+        return x.contiguous()
+    assert x.dtype == torch.float32
+    xc = x.contiguous()
+    out = torch.empty(xc.shape, dtype=torch.bfloat16, device=x.device)
+    check(lib().vf_cast_f32_to_bf16(xc.data_ptr(), out.data_ptr(), xc.numel(), _stream()), "vf_cast_f32_to_bf16")
+    return out
+
+
+def to_f32(x):
+    _require_cuda(x)
+    if x.dtype == torch.float32:
+        return x.contiguous()
+    assert x.dtype == torch.bfloat16
+    xc = x.contiguous()
+    out = torch.empty(xc.shape, dtype=torch.float32, device=x.device)
+    check(lib().vf_cast_bf16_to_f32(xc.data_ptr(), out.data_ptr(), xc.numel(), _stream()), "vf_cast_bf16_to_f32")
+    return out

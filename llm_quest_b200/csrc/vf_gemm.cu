@@ -1,0 +1,553 @@
+// vf_gemm.cu — persistent warp-specialised tcgen05 GEMM for sm_100a.
+//
+//   out = epilogue(A[M,K] · W[N,K]^T)      A, W bf16 (K-major), fp32 accumulation in TMEM.
+//
+// Replaces every nn.Linear / nn.ConvNd(k=s) on the reference's vision path (see include/vfuse.h
+// for the call-site list). Design:
+//   * one CTA per SM, static round-robin over 128 x BN output tiles (n fastest so that concurrently
+//     running CTAs share the same A rows in L2);
+//   * warp 0 / lane 0: TMA producer, 4-stage ring of {A 128x64, W BNx64} bf16 tiles, 128B swizzle;
+//   * warp 1 / lane 0: tcgen05.mma issuer (cta_group::1, M=128, N=BN, K=16 per instruction),
+//     accumulators double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps the
+//     main loop of tile i+1;
+//   * warps 2..5: epilogue. tcgen05.ld 32x32b gives every thread one output row, so bias, GELU,
+//     residual add, axial RoPE (pairs i / i+32 of a head live in the same thread) and the row
+//     remaps are all register-local.
+//   * patch-embedding mode gathers the A tile with ONE 5-D TMA box per stage straight from the
+//     [B,C,T,H,W] pixel tensor (im2col-free): tile rows are a PH x PW rectangle of patches.
+#include "vf_common.cuh"
+#include "../../include/vfuse.h"
+
+#include <math.h>
+
+namespace vf {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int STAGES = 4;
+constexpr int GEMM_THREADS = 192;  // warp0 TMA, warp1 MMA, warps 2-5 epilogue
+
+struct GemmParams {
+  int M, N, K;
+  int num_m_blk, num_n_blk, num_kb;
+  const float* bias;
+  void* out;
+  long long ldo;
+  const float* res;
+  long long ldr;
+  int grp_rows;
+  long long grp_stride;
+  long long row_off;
+  const float* rope_cos;
+  const float* rope_sin;
+  int rope_period;
+  int rope_cols;
+  const int* dst_rows;
+  // patch-embedding mode
+  int patch;
+  int PW, PH;          // tile rectangle in patches (PW*PH == 128)
+  int nw, nh;          // patches per row / column of one frame
+  int n_pwb, n_phb;    // tile rectangles per frame
+  int Tp, T, C, tp, P; // frames after temporal merge, raw frames, channels, temporal patch, patch
+  const float* pos;
+  long long ld_pos;
+};
+
+template <int BN>
+struct SmemLayout {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFF + 256 + 1024;  // barriers + alignment slack
+};
+
+__device__ __forceinline__ void wait_or_trap(uint64_t* bar, uint32_t parity) {
+  // Bounded wait: a protocol bug becomes a trap (CUDA error) instead of a hung GPU.
+  long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      printf("vf_gemm: mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
+}
+
+__device__ __forceinline__ float gelu_tanh_f(float x) {
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  float u = k0 * x * fmaf(k1, x * x, 1.0f);
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
+  return 0.5f * x * (1.0f + t);
+}
+__device__ __forceinline__ float gelu_erf_f(float x) {
+  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
+}
+
+template <int EPI, int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
+            const __grid_constant__ CUtensorMap tmB) {
+  using L = SmemLayout<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;   // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;       // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.num_m_blk * p.num_n_blk;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], 4);  // one arrival per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<2 * BN>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int n_blk = tile % p.num_n_blk;
+        const int m_blk = tile / p.num_n_blk;
+        int pc2 = 0, pc3 = 0, pimg = 0;  // patch mode: pw0, ph0, (b*C)*T + t'*tp
+        if (p.patch) {
+          int t = m_blk;
+          const int pwb = t % p.n_pwb; t /= p.n_pwb;
+          const int phb = t % p.n_phb; t /= p.n_phb;
+          const int tpr = t % p.Tp;
+          const int b = t / p.Tp;
+          pc2 = pwb * p.PW;
+          pc3 = phb * p.PH;
+          pimg = b * p.C * p.T + tpr * p.tp;
+        }
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          wait_or_trap(&empty_bar[stage], phase ^ 1);
+          uint8_t* a_dst = smem + stage * L::STAGE_BYTES;
+          uint8_t* b_dst = a_dst + L::A_BYTES;
+          mbar_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+          if (p.patch) {
+            // K index = ((c*tp + dt)*P + py)*P + px ; one 64-wide k-block = (64/P) pixel rows.
+            const int rows_per_kb = BK / p.P;
+            const int kb_per_plane = p.P / rows_per_kb;       // k-blocks per (c,dt) plane
+            const int plane = kb / kb_per_plane;              // c*tp + dt
+            const int py0 = (kb % kb_per_plane) * rows_per_kb;
+            const int c = plane / p.tp, dt = plane % p.tp;
+            tma_load_5d(a_dst, &tmA, &full_bar[stage], 0, py0, pc2, pc3, pimg + c * p.T + dt);
+          } else {
+            tma_load_2d(a_dst, &tmA, &full_bar[stage], kb * BK, m_blk * BM);
+          }
+          tma_load_2d(b_dst, &tmB, &full_bar[stage], kb * BK, n_blk * BN);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        wait_or_trap(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          wait_or_trap(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * L::STAGE_BYTES);
+          const uint64_t a_desc = umma_desc_sw128(a_addr);
+          const uint64_t b_desc = umma_desc_sw128(a_addr + L::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // advance 16 bf16 = 32 B inside the 128 B swizzle atom: +2 in the (addr>>4) field
+            umma_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+          }
+          umma_commit(&empty_bar[stage]);  // smem slot is free once these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull_bar[acc]);      // accumulator complete
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int n_blk = tile % p.num_n_blk;
+      const int m_blk = tile / p.num_n_blk;
+      const int r_local = quarter * 32 + lane;
+
+      // ---- which output row does this thread own?
+      bool row_ok;
+      long long out_row;
+      const float* pos_row = nullptr;
+      if (p.patch) {
+        int t = m_blk;
+        const int pwb = t % p.n_pwb; t /= p.n_pwb;
+        const int phb = t % p.n_phb; t /= p.n_phb;
+        const int tpr = t % p.Tp;
+        const int b = t / p.Tp;
+        const int ph = phb * p.PH + r_local / p.PW;
+        const int pw = pwb * p.PW + r_local % p.PW;
+        row_ok = (ph < p.nh) && (pw < p.nw);
+        const int sp = ph * p.nw + pw;
+        out_row = (long long)b * p.grp_stride + p.row_off + (long long)tpr * p.nh * p.nw + sp;
+        if (p.pos) pos_row = p.pos + (long long)sp * p.ld_pos;
+      } else {
+        const int m = m_blk * BM + r_local;
+        row_ok = m < p.M;
+        if (EPI == VF_EPI_SCATTER_BF16) {
+          const int d = row_ok ? p.dst_rows[m] : -1;
+          row_ok = d >= 0;
+          out_row = d;
+        } else if (p.grp_rows > 0) {
+          out_row = (long long)(m / p.grp_rows) * p.grp_stride + (m % p.grp_rows) + p.row_off;
+        } else {
+          out_row = m;
+        }
+      }
+
+      wait_or_trap(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
+      const int col0 = n_blk * BN;
+
+      if constexpr (EPI == VF_EPI_QKV_ROPE_BF16) {
+        const int m = m_blk * BM + r_local;
+        const int prow = m % p.rope_period;
+        const float4* cs = reinterpret_cast<const float4*>(p.rope_cos + (long long)prow * 32);
+        const float4* sn = reinterpret_cast<const float4*>(p.rope_sin + (long long)prow * 32);
+        __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) + out_row * p.ldo;
+#pragma unroll 1
+        for (int h = 0; h < BN / 64; ++h) {
+          __syncwarp();
+          const int hc = col0 + h * 64;
+          const bool rot = hc < p.rope_cols;
+#pragma unroll
+          for (int sub = 0; sub < 2; ++sub) {  // 16 pairs at a time
+            uint32_t x1[16], x2[16];
+            tmem_ld_x16(t_row + h * 64 + sub * 16, x1);
+            tmem_ld_x16(t_row + h * 64 + 32 + sub * 16, x2);
+            tmem_ld_wait();
+            uint32_t o1[8], o2[8];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              float a[4], b[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int j = q * 4 + e;
+                const int c1 = hc + sub * 16 + j;
+                a[e] = __uint_as_float(x1[j]) + (p.bias && c1 < p.N ? p.bias[c1] : 0.f);
+                b[e] = __uint_as_float(x2[j]) + (p.bias && c1 + 32 < p.N ? p.bias[c1 + 32] : 0.f);
+              }
+              if (rot && row_ok) {
+                const float4 c4 = cs[sub * 4 + q];
+                const float4 s4 = sn[sub * 4 + q];
+                const float cc[4] = {c4.x, c4.y, c4.z, c4.w};
+                const float ss[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float ra = a[e] * cc[e] - b[e] * ss[e];
+                  const float rb = b[e] * cc[e] + a[e] * ss[e];
+                  a[e] = ra;
+                  b[e] = rb;
+                }
+              }
+              o1[q * 2 + 0] = pack_bf16(a[0], a[1]);
+              o1[q * 2 + 1] = pack_bf16(a[2], a[3]);
+              o2[q * 2 + 0] = pack_bf16(b[0], b[1]);
+              o2[q * 2 + 1] = pack_bf16(b[2], b[3]);
+            }
+            if (row_ok && hc + 64 <= p.N) {
+              uint4* d1 = reinterpret_cast<uint4*>(orow + hc + sub * 16);
+              uint4* d2 = reinterpret_cast<uint4*>(orow + hc + 32 + sub * 16);
+              d1[0] = make_uint4(o1[0], o1[1], o1[2], o1[3]);
+              d1[1] = make_uint4(o1[4], o1[5], o1[6], o1[7]);
+              d2[0] = make_uint4(o2[0], o2[1], o2[2], o2[3]);
+              d2[1] = make_uint4(o2[4], o2[5], o2[6], o2[7]);
+            }
+          }
+        }
+      } else {
+        constexpr bool OUT_F32 = (EPI == VF_EPI_BIAS_F32 || EPI == VF_EPI_BIAS_RES_F32);
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          __syncwarp();
+          uint32_t r[32];
+          tmem_ld_x32(t_row + c * 32, r);
+          tmem_ld_wait();
+          const int cbase = col0 + c * 32;
+          if (!row_ok || cbase >= p.N) continue;
+          const bool full = (cbase + 32 <= p.N);
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float x = __uint_as_float(r[j]);
+            if (p.bias && (full || cbase + j < p.N)) x += __ldg(p.bias + cbase + j);
+            v[j] = x;
+          }
+          if (pos_row) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (full || cbase + j < p.N) v[j] += __ldg(pos_row + cbase + j);
+          }
+          if constexpr (EPI == VF_EPI_BIAS_RES_F32) {
+            const float* rrow = p.res + out_row * p.ldr + cbase;
+            if (full) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 t4 = reinterpret_cast<const float4*>(rrow)[j];
+                v[j * 4 + 0] += t4.x; v[j * 4 + 1] += t4.y; v[j * 4 + 2] += t4.z; v[j * 4 + 3] += t4.w;
+              }
+            } else {
+              for (int j = 0; j < 32; ++j) if (cbase + j < p.N) v[j] += rrow[j];
+            }
+          }
+          if constexpr (EPI == VF_EPI_GELU_TANH_BF16) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = gelu_tanh_f(v[j]);
+          }
+          if constexpr (EPI == VF_EPI_GELU_ERF_BF16) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = gelu_erf_f(v[j]);
+          }
+          if constexpr (OUT_F32) {
+            float* orow = reinterpret_cast<float*>(p.out) + out_row * p.ldo + cbase;
+            if (full) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                reinterpret_cast<float4*>(orow)[j] = make_float4(v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]);
+            } else {
+              for (int j = 0; j < 32; ++j) if (cbase + j < p.N) orow[j] = v[j];
+            }
+          } else {
+            __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) + out_row * p.ldo + cbase;
+            if (full) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                reinterpret_cast<uint4*>(orow)[j] =
+                    make_uint4(pack_bf16(v[j * 8 + 0], v[j * 8 + 1]), pack_bf16(v[j * 8 + 2], v[j * 8 + 3]),
+                               pack_bf16(v[j * 8 + 4], v[j * 8 + 5]), pack_bf16(v[j * 8 + 6], v[j * 8 + 7]));
+            } else {
+              for (int j = 0; j < 32; ++j) if (cbase + j < p.N) orow[j] = __float2bfloat16_rn(v[j]);
+            }
+          }
+        }
+      }
+      // release the accumulator buffer
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<2 * BN>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+template <int EPI, int BN>
+static int launch_gemm(const GemmParams& p, const CUtensorMap& tmA, const CUtensorMap& tmB,
+                       cudaStream_t stream) {
+  using L = SmemLayout<BN>;
+  static bool configured = false;
+  auto kfn = gemm_kernel<EPI, BN>;
+  if (!configured) {
+    VF_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    configured = true;
+  }
+  const int sms = device_sm_count();
+  VF_REQUIRE(sms > 0, VF_ERR_NO_DEVICE, "no CUDA device");
+  const int tiles = p.num_m_blk * p.num_n_blk;
+  const int grid = tiles < sms ? tiles : sms;
+  kfn<<<grid, GEMM_THREADS, L::TOTAL, stream>>>(p, tmA, tmB);
+  count_launch();
+  VF_CUDA(cudaGetLastError());
+  return VF_OK;
+}
+
+template <int BN>
+static int dispatch_epi(int mode, const GemmParams& p, const CUtensorMap& a, const CUtensorMap& b,
+                        cudaStream_t s) {
+  switch (mode) {
+    case VF_EPI_BIAS_BF16: return launch_gemm<VF_EPI_BIAS_BF16, BN>(p, a, b, s);
+    case VF_EPI_BIAS_F32: return launch_gemm<VF_EPI_BIAS_F32, BN>(p, a, b, s);
+    case VF_EPI_BIAS_RES_F32: return launch_gemm<VF_EPI_BIAS_RES_F32, BN>(p, a, b, s);
+    case VF_EPI_GELU_TANH_BF16: return launch_gemm<VF_EPI_GELU_TANH_BF16, BN>(p, a, b, s);
+    case VF_EPI_GELU_ERF_BF16: return launch_gemm<VF_EPI_GELU_ERF_BF16, BN>(p, a, b, s);
+    case VF_EPI_QKV_ROPE_BF16: return launch_gemm<VF_EPI_QKV_ROPE_BF16, BN>(p, a, b, s);
+    case VF_EPI_SCATTER_BF16: return launch_gemm<VF_EPI_SCATTER_BF16, BN>(p, a, b, s);
+    default: break;
+  }
+  set_last_error("vf_gemm_bf16: unknown epilogue mode %d", mode);
+  return VF_ERR_ARG;
+}
+
+static int pick_bn(int M, int N) {
+  // 256-wide tiles halve the number of A re-reads and MMA issue overhead; use 128 when N is small
+  // or when 256-wide tiles would leave most SMs idle.
+  if (N <= 128) return 128;
+  const long long tiles256 = (long long)((M + BM - 1) / BM) * ((N + 255) / 256);
+  if (tiles256 < 100 && N > 128) return 128;
+  return 256;
+}
+
+}  // namespace vf
+
+using namespace vf;
+
+extern "C" int vf_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, int32_t M,
+                            int32_t N, int32_t K, const vf_epilogue* ep, void* stream) {
+  VF_REQUIRE(A && W && ep && ep->out, VF_ERR_ARG, "vf_gemm_bf16: null pointer");
+  VF_REQUIRE(M > 0 && N > 0 && K > 0, VF_ERR_ARG, "vf_gemm_bf16: bad shape M=%d N=%d K=%d", M, N, K);
+  VF_REQUIRE(lda >= K && ldw >= K, VF_ERR_ARG, "vf_gemm_bf16: lda/ldw smaller than K");
+  VF_REQUIRE((lda % 8) == 0 && (ldw % 8) == 0, VF_ERR_ALIGN,
+             "vf_gemm_bf16: row pitches must be multiples of 8 elements (16 B) for TMA");
+  VF_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0,
+             VF_ERR_ALIGN, "vf_gemm_bf16: A/W must be 16-byte aligned");
+  const bool out_f32 = ep->mode == VF_EPI_BIAS_F32 || ep->mode == VF_EPI_BIAS_RES_F32;
+  VF_REQUIRE((reinterpret_cast<uintptr_t>(ep->out) & 15) == 0 && (ep->ldo % (out_f32 ? 4 : 8)) == 0,
+             VF_ERR_ALIGN, "vf_gemm_bf16: out must be 16-byte aligned with a 16-byte multiple pitch");
+  if (ep->mode == VF_EPI_BIAS_RES_F32)
+    VF_REQUIRE(ep->res && (reinterpret_cast<uintptr_t>(ep->res) & 15) == 0 && (ep->ldr % 4) == 0,
+               VF_ERR_ARG, "vf_gemm_bf16: residual pointer missing or misaligned");
+  if (ep->mode == VF_EPI_QKV_ROPE_BF16)
+    VF_REQUIRE(ep->rope_cos && ep->rope_sin && ep->rope_period > 0 && (ep->rope_cols % 64) == 0 &&
+                   (N % 64) == 0,
+               VF_ERR_ARG, "vf_gemm_bf16: rope epilogue needs cos/sin, period>0, N and rope_cols %% 64 == 0");
+  if (ep->mode == VF_EPI_SCATTER_BF16)
+    VF_REQUIRE(ep->dst_rows, VF_ERR_ARG, "vf_gemm_bf16: scatter epilogue needs dst_rows");
+
+  GemmParams p{};
+  p.M = M; p.N = N; p.K = K;
+  const int bn = pick_bn(M, N);
+  p.num_m_blk = (M + BM - 1) / BM;
+  p.num_n_blk = (N + bn - 1) / bn;
+  p.num_kb = (K + BK - 1) / BK;
+  p.bias = ep->bias;
+  p.out = ep->out; p.ldo = ep->ldo;
+  p.res = ep->res; p.ldr = ep->ldr;
+  p.grp_rows = ep->grp_rows; p.grp_stride = ep->grp_stride; p.row_off = ep->row_off;
+  p.rope_cos = ep->rope_cos; p.rope_sin = ep->rope_sin;
+  p.rope_period = ep->rope_period; p.rope_cols = ep->rope_cols;
+  p.dst_rows = ep->dst_rows;
+
+  CUtensorMap tmA, tmB;
+  {
+    uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
+    uint64_t strides[1] = {(uint64_t)lda * 2};
+    uint32_t box[2] = {BK, BM};
+    int e = encode_tmap(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, A, dims, strides, box,
+                        CU_TENSOR_MAP_SWIZZLE_128B);
+    if (e) return e;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)K, (uint64_t)N};
+    uint64_t strides[1] = {(uint64_t)ldw * 2};
+    uint32_t box[2] = {BK, (uint32_t)bn};
+    int e = encode_tmap(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, W, dims, strides, box,
+                        CU_TENSOR_MAP_SWIZZLE_128B);
+    if (e) return e;
+  }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  return bn == 256 ? dispatch_epi<256>(ep->mode, p, tmA, tmB, s)
+                   : dispatch_epi<128>(ep->mode, p, tmA, tmB, s);
+}
+
+extern "C" int vf_patch_embed(const void* pixels, int32_t B, int32_t C, int32_t T, int32_t H,
+                              int32_t W, int32_t P, int32_t tp, const void* weight,
+                              const float* bias, const float* pos, int64_t ld_pos, int32_t N,
+                              float* out, int64_t ldo, int64_t out_rows_per_sample,
+                              int64_t out_row_off, void* stream) {
+  VF_REQUIRE(pixels && weight && out, VF_ERR_ARG, "vf_patch_embed: null pointer");
+  VF_REQUIRE(B > 0 && C > 0 && T > 0 && H > 0 && W > 0 && N > 0, VF_ERR_ARG, "vf_patch_embed: bad shape");
+  VF_REQUIRE(P == 8 || P == 16 || P == 32, VF_ERR_ARG,
+             "vf_patch_embed: patch size %d unsupported (TMA path needs 8, 16 or 32)", P);
+  VF_REQUIRE(tp >= 1 && T % tp == 0 && H % P == 0 && W % P == 0, VF_ERR_ARG,
+             "vf_patch_embed: T/H/W not divisible by the patch shape");
+  VF_REQUIRE((W % 8) == 0, VF_ERR_ALIGN, "vf_patch_embed: image width must be a multiple of 8 pixels");
+  VF_REQUIRE((reinterpret_cast<uintptr_t>(pixels) & 15) == 0 && (reinterpret_cast<uintptr_t>(weight) & 15) == 0 &&
+                 (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (ldo % 4) == 0,
+             VF_ERR_ALIGN, "vf_patch_embed: pointers must be 16-byte aligned");
+  const int K = C * tp * P * P;
+  VF_REQUIRE(K % BK == 0, VF_ERR_ARG, "vf_patch_embed: C*tp*P*P must be a multiple of 64");
+  const int nh = H / P, nw = W / P, Tp = T / tp;
+
+  // tile rectangle: PW = smallest of {4,8,16,32} that wastes the least of the frame width
+  int best_pw = 32;
+  double best_eff = -1.0;
+  for (int pw = 4; pw <= 32; pw *= 2) {
+    const int ph = BM / pw;
+    const int nb_w = (nw + pw - 1) / pw, nb_h = (nh + ph - 1) / ph;
+    const double eff = double(nw) * nh / (double(nb_w) * pw * nb_h * ph);
+    if (eff > best_eff + 1e-9) { best_eff = eff; best_pw = pw; }
+  }
+  GemmParams p{};
+  p.patch = 1;
+  p.PW = best_pw; p.PH = BM / best_pw;
+  p.nw = nw; p.nh = nh;
+  p.n_pwb = (nw + p.PW - 1) / p.PW;
+  p.n_phb = (nh + p.PH - 1) / p.PH;
+  p.Tp = Tp; p.T = T; p.C = C; p.tp = tp; p.P = P;
+  p.pos = pos; p.ld_pos = ld_pos;
+  p.M = B * Tp * nh * nw; p.N = N; p.K = K;
+  const int bn = N <= 128 ? 128 : 256;
+  p.num_m_blk = B * Tp * p.n_phb * p.n_pwb;
+  p.num_n_blk = (N + bn - 1) / bn;
+  p.num_kb = K / BK;
+  p.bias = bias;
+  p.out = out; p.ldo = ldo;
+  p.grp_stride = out_rows_per_sample; p.row_off = out_row_off;
+
+  CUtensorMap tmA, tmB;
+  {
+    // dims (fastest first): px[P], py[P], pw[nw], ph[nh], image plane [B*C*T]
+    uint64_t dims[5] = {(uint64_t)P, (uint64_t)P, (uint64_t)nw, (uint64_t)nh, (uint64_t)B * C * T};
+    uint64_t strides[4] = {(uint64_t)W * 2, (uint64_t)P * 2, (uint64_t)W * P * 2, (uint64_t)H * W * 2};
+    uint32_t box[5] = {(uint32_t)P, (uint32_t)(BK / P), (uint32_t)p.PW, (uint32_t)p.PH, 1};
+    int e = encode_tmap(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, pixels, dims, strides, box,
+                        CU_TENSOR_MAP_SWIZZLE_128B);
+    if (e) return e;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)K, (uint64_t)N};
+    uint64_t strides[1] = {(uint64_t)K * 2};
+    uint32_t box[2] = {BK, (uint32_t)bn};
+    int e = encode_tmap(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, weight, dims, strides, box,
+                        CU_TENSOR_MAP_SWIZZLE_128B);
+    if (e) return e;
+  }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  return bn == 256 ? launch_gemm<VF_EPI_BIAS_F32, 256>(p, tmA, tmB, s)
+                   : launch_gemm<VF_EPI_BIAS_F32, 128>(p, tmA, tmB, s);
+}

@@ -1,0 +1,66 @@
+"""Part-1 ViT multi-head attention on libvfuse kernels.
+
+Drop-in for ``ViTMultiHeadAttention`` of the reference's
+``llm_quest/multimodal/vision_transformer/vit_attention.py`` (:8-91): separate ``w_queries`` /
+``w_keys`` / ``w_values`` / ``out_proj`` Linear parameters (same ``state_dict`` keys), no mask,
+softmax(QK^T * head_dim^-0.5) V. The three projection weights are packed once into one [3D, D]
+bf16 matrix so a single GEMM feeds the fused attention kernel.
+"""
+
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from ... import _lib
+from ..._lib import VF_EPI_BIAS_BF16, VF_EPI_BIAS_F32, VFuseError
+from ...qwen.qwen3_5.qwen3_5_vision_model import _Packed, _as_2d_bf16, _f32, _forward_only_guard, _w_bf16
+
+
+class ViTMultiHeadAttention(nn.Module):
+    def __init__(self, d_in, d_out, dropout, num_heads, qkv_bias=False):
+        super().__init__()
+        if d_out % num_heads != 0:
+            raise ValueError("d_out must be divisible by num_heads")
+        self.d_out = d_out
+        self.num_heads = num_heads
+        self.head_dim = d_out // num_heads
+        self.att_scaling = self.head_dim**-0.5
+        self.w_queries = nn.Linear(d_in, d_out, bias=qkv_bias)
+        self.w_keys = nn.Linear(d_in, d_out, bias=qkv_bias)
+        self.w_values = nn.Linear(d_in, d_out, bias=qkv_bias)
+        self.dropout = nn.Dropout(dropout)
+        self.out_proj = nn.Linear(d_out, d_out)
+        self._packed = _Packed()
+
+    def packed_qkv(self):
+        ws = [self.w_queries.weight, self.w_keys.weight, self.w_values.weight]
+        bs = [self.w_queries.bias, self.w_keys.bias, self.w_values.bias]
+        w = self._packed.get("wqkv", ws, lambda: torch.cat([t.detach() for t in ws], 0).to(torch.bfloat16).contiguous())
+        b = None
+        if bs[0] is not None:
+            b = self._packed.get("bqkv", bs, lambda: torch.cat([t.detach() for t in bs], 0).float().contiguous())
+        return w, b
+
+    def packed_out(self):
+        return _w_bf16(self._packed, "wo", self.out_proj.weight), _f32(self._packed, "bo", self.out_proj.bias)
+
+    def attend(self, h2d, B, S):
+        """h2d bf16 [B*S, d_in] -> context bf16 [B*S, d_out]."""
+        if self.head_dim != 64:
+            raise VFuseError(f"the fused attention kernel is built for head_dim 64, got {self.head_dim}")
+        w, b = self.packed_qkv()
+        qkv = torch.empty((B * S, 3 * self.d_out), dtype=torch.bfloat16, device=h2d.device)
+        _lib.gemm(h2d, w, VF_EPI_BIAS_BF16, qkv, bias=b)
+        ctx = torch.empty((B * S, self.d_out), dtype=torch.bfloat16, device=h2d.device)
+        _lib.attention(qkv, ctx, B, S, self.num_heads, self.att_scaling)
+        return ctx
+
+    def forward(self, x):
+        _forward_only_guard(self)
+        b, seq_len, d_in = x.shape
+        ctx = self.attend(_as_2d_bf16(x), b, seq_len)
+        wo, bo = self.packed_out()
+        out = torch.empty((b * seq_len, self.d_out), dtype=torch.float32, device=x.device)
+        _lib.gemm(ctx, wo, VF_EPI_BIAS_F32, out, bias=bo)
+        return out.view(b, seq_len, self.d_out).to(x.dtype)

@@ -1,0 +1,361 @@
+"""GPU parity tests, kernel by kernel, through the C ABI (ctypes) against the CPU oracle.
+
+Tolerances (BASELINE.json north_star): integer / index / placement work bit-exact; floating point
+max|delta|/max|ref| <= 1e-2 and cosine >= 0.9999 against the fp32 oracle — single kernels are held to
+much tighter bounds here (bf16 operands, fp32 accumulation: a few 1e-3).
+"""
+
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import fusion_oracle as FO
+from oracle import vision_oracle as VO
+
+pytestmark = pytest.mark.gpu
+IMG = 248056
+
+
+@pytest.fixture(scope="module")
+def L():
+    from llm_quest_b200 import _lib
+
+    _lib.lib()
+    return _lib
+
+
+def dev(t):
+    return t.cuda()
+
+
+def bf(t):
+    return t.to(torch.bfloat16)
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*shape, generator=g) * scale
+
+
+def check_close(got, ref, tol=1e-2, cos=0.9999, what=""):
+    got, ref = got.float().cpu(), ref.float().cpu()
+    assert got.shape == ref.shape, (got.shape, ref.shape)
+    assert torch.isfinite(got).all(), f"{what}: non-finite output"
+    e, c = VO.max_norm_err(got, ref), VO.cosine(got, ref)
+    print(f"{what}: max_norm_err={e:.3e} cosine={c:.7f}")
+    assert e <= tol and c >= cos, f"{what}: err {e:.3e} cos {c:.6f}"
+
+
+# ------------------------------------------------------------------------------------------------
+# GEMM + epilogues
+# ------------------------------------------------------------------------------------------------
+GEMM_SHAPES = [(128, 256, 64), (300, 768, 768), (1000, 2304, 768), (257, 100, 768), (8, 1024, 3072), (4096, 3072, 768)]
+
+
+@pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
+def test_gemm_bias_f32(L, M, N, K):
+    a, w, b = bf(rnd(M, K, seed=1)), bf(rnd(N, K, seed=2, scale=0.05)), rnd(N, seed=3)
+    out = torch.full((M, N), float("nan"), device="cuda")
+    L.gemm(dev(a), dev(w), L.VF_EPI_BIAS_F32, out, bias=dev(b))
+    check_close(out, a.float() @ w.float().t() + b, tol=2e-3, what=f"gemm_f32 {M}x{N}x{K}")
+
+
+def test_gemm_no_bias_bf16_and_strided_a(L):
+    M, N, K = 200, 512, 256
+    big = bf(rnd(M, 2 * K, seed=4))
+    a = big[:, :K]  # row stride 2K
+    w = bf(rnd(N, K, seed=5, scale=0.05))
+    out = torch.zeros((M, N), dtype=torch.bfloat16, device="cuda")
+    L.gemm(dev(big)[:, :K], dev(w), L.VF_EPI_BIAS_BF16, out)
+    check_close(out, a.float() @ w.float().t(), tol=6e-3, what="gemm_bf16 strided A")
+
+
+def test_gemm_residual_inplace(L):
+    M, N, K = 777, 768, 3072
+    a, w, b = bf(rnd(M, K, seed=6)), bf(rnd(N, K, seed=7, scale=0.02)), rnd(N, seed=8)
+    res = rnd(M, N, seed=9)
+    x = dev(res.clone())
+    L.gemm(dev(a), dev(w), L.VF_EPI_BIAS_RES_F32, x, bias=dev(b), res=x)
+    check_close(x, a.float() @ w.float().t() + b + res, tol=2e-3, what="gemm residual in-place")
+
+
+@pytest.mark.parametrize("mode,fn", [("tanh", VO.gelu_tanh), ("erf", VO.gelu_erf)])
+def test_gemm_gelu(L, mode, fn):
+    M, N, K = 640, 3072, 768
+    a, w, b = bf(rnd(M, K, seed=10)), bf(rnd(N, K, seed=11, scale=0.05)), rnd(N, seed=12)
+    out = torch.zeros((M, N), dtype=torch.bfloat16, device="cuda")
+    L.gemm(dev(a), dev(w), L.VF_EPI_GELU_TANH_BF16 if mode == "tanh" else L.VF_EPI_GELU_ERF_BF16, out, bias=dev(b))
+    check_close(out, fn(a.float() @ w.float().t() + b), tol=6e-3, what=f"gemm gelu_{mode}")
+
+
+def test_gemm_qkv_rope(L):
+    nh, nw, frames, B, H = 5, 3, 2, 3, 2
+    n, D = nh * nw, 128
+    S = frames * n
+    M = B * S
+    a, w, b = bf(rnd(M, D, seed=13)), bf(rnd(3 * D, D, seed=14, scale=0.08)), rnd(3 * D, seed=15)
+    cos, sin = VO.axial_rope_tables(10_000, 64, nh, nw)
+    out = torch.zeros((M, 3 * D), dtype=torch.bfloat16, device="cuda")
+    L.gemm(dev(a), dev(w), L.VF_EPI_QKV_ROPE_BF16, out, bias=dev(b),
+           rope=(dev(cos[:, :32].contiguous()), dev(sin[:, :32].contiguous()), n, 2 * D))
+    qkv = (a.float() @ w.float().t() + b).view(B, S, 3, H, 64)
+    q, k, v = (qkv[:, :, i].transpose(1, 2) for i in range(3))
+    cs, sn = cos.repeat(frames, 1), sin.repeat(frames, 1)
+    q, k = VO.rotate_half_apply(q, cs, sn), VO.rotate_half_apply(k, cs, sn)
+    ref = torch.stack([t.transpose(1, 2) for t in (q, k, v)], dim=2).reshape(M, 3 * D)
+    check_close(out, ref, tol=6e-3, what="gemm qkv+rope")
+
+
+def test_gemm_row_remap_and_scatter(L):
+    M, N, K = 30, 256, 128
+    a, w = bf(rnd(M, K, seed=16)), bf(rnd(N, K, seed=17, scale=0.1))
+    ref = a.float() @ w.float().t()
+    fused = torch.zeros((3, 25, N), device="cuda")  # 3 samples x (10 vision + 15 text) rows
+    L.gemm(dev(a), dev(w), L.VF_EPI_BIAS_F32, fused.view(-1, N), grp_rows=10, grp_stride=25, row_off=0)
+    got = fused.cpu()
+    check_close(got[:, :10].reshape(M, N), ref, tol=2e-3, what="gemm row remap")
+    assert (got[:, 10:] == 0).all()
+    dst = torch.full((M,), -1, dtype=torch.int32)
+    perm = torch.randperm(64, generator=torch.Generator().manual_seed(1))[:M].to(torch.int32)
+    dst[: M - 3] = perm[: M - 3]
+    out = torch.zeros((64, N), dtype=torch.bfloat16, device="cuda")
+    L.gemm(dev(a), dev(w), L.VF_EPI_SCATTER_BF16, out, dst_rows=dev(dst))
+    got = out.float().cpu()
+    exp = torch.zeros(64, N)
+    exp[dst[: M - 3].long()] = ref[: M - 3]
+    check_close(got, exp, tol=6e-3, what="gemm scatter")
+    untouched = torch.ones(64, dtype=torch.bool)
+    untouched[dst[: M - 3].long()] = False
+    assert (got[untouched] == 0).all()
+
+
+# ------------------------------------------------------------------------------------------------
+# patch embedding (im2col-free TMA gather)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,T,H,W,D", [(2, 2, 64, 96, 128), (3, 4, 448, 448, 768), (1, 2, 224, 224, 256), (2, 2, 160, 48, 128)])
+def test_patch_embed3d(L, B, T, H, W, D):
+    P, tp = 16, 2
+    x = bf(rnd(B, 3, T, H, W, seed=20))
+    w = bf(rnd(D, 3, tp, P, P, seed=21, scale=0.03))
+    b = rnd(D, seed=22)
+    n = (H // P) * (W // P)
+    pos = rnd(n + 5, D, seed=23)
+    S = (T // tp) * n
+    out = torch.full((B * S, D), float("nan"), device="cuda")
+    L.patch_embed(dev(x), dev(w.reshape(D, -1).contiguous()), dev(b), dev(pos), out, P, tp, S, 0)
+    ref = VO.patch_embed3d(x.float(), w.float(), b) + pos[:n].repeat(T // tp, 1)[None]
+    check_close(out.view(B, S, D), ref, tol=2e-3, what=f"patch_embed3d {B}x{T}x{H}x{W}")
+
+
+def test_patch_embed2d_with_cls_rows(L):
+    B, H, W, D, P = 3, 224, 224, 768, 16
+    x, w, b = bf(rnd(B, 3, H, W, seed=24)), bf(rnd(D, 3, P, P, seed=25, scale=0.03)), rnd(D, seed=26)
+    n = (H // P) * (W // P)
+    pos, cls = rnd(n + 1, D, seed=27), rnd(D, seed=28)
+    out = torch.full((B * (n + 1), D), float("nan"), device="cuda")
+    L.patch_embed(dev(x).unsqueeze(2), dev(w.reshape(D, -1).contiguous()), dev(b), dev(pos)[1:], out, P, 1, n + 1, 1)
+    L.vit_cls_pos(dev(cls), dev(pos)[0], out, B, n + 1, D)
+    ref = VO.patch_embed3d(x.float().unsqueeze(2), w.float().unsqueeze(2), b)
+    ref = torch.cat([cls.expand(B, 1, D), ref], dim=1) + pos[None]
+    check_close(out.view(B, n + 1, D), ref, tol=2e-3, what="patch_embed2d+cls")
+
+
+# ------------------------------------------------------------------------------------------------
+# attention
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,S,H", [(2, 128, 2), (3, 196, 2), (2, 197, 12), (1, 784, 3), (2, 24, 1), (1, 1000, 2), (1, 3136, 1)])
+def test_attention(L, B, S, H):
+    qkv = bf(rnd(B * S, 3 * H * 64, seed=30 + S))
+    out = torch.full((B * S, H * 64), float("nan"), dtype=torch.bfloat16, device="cuda")
+    L.attention(dev(qkv), out, B, S, H, 1 / 8)
+    q, k, v = (qkv.float().view(B, S, 3, H, 64)[:, :, i].transpose(1, 2) for i in range(3))
+    ref = (torch.softmax(q @ k.transpose(-1, -2) / 8, -1) @ v).transpose(1, 2).reshape(B * S, H * 64)
+    check_close(out, ref, tol=8e-3, what=f"attention B{B} S{S} H{H}")
+
+
+def test_attention_large_scores_trigger_lazy_rescale(L):
+    """Rows whose max grows tile after tile exercise the in-TMEM O rescale."""
+    B, S, H = 1, 640, 1
+    qkv = rnd(S, 192, seed=40)
+    ramp = torch.linspace(0, 6, S)[:, None]
+    qkv[:, 64:128] = qkv[:, 64:128] * 0.2 + ramp * torch.sign(qkv[:1, :64])  # keys align more and more with q
+    qkv[:, :64] = qkv[:1, :64].expand(S, 64) * 2 + 0.1 * qkv[:, :64]
+    qkv = bf(qkv)
+    out = torch.zeros((S, 64), dtype=torch.bfloat16, device="cuda")
+    L.attention(dev(qkv), out, B, S, H, 1 / 8)
+    q, k, v = (qkv.float().view(1, S, 3, 1, 64)[:, :, i].transpose(1, 2) for i in range(3))
+    ref = (torch.softmax(q @ k.transpose(-1, -2) / 8, -1) @ v).transpose(1, 2).reshape(S, 64)
+    check_close(out, ref, tol=1e-2, what="attention rescale")
+
+
+# ------------------------------------------------------------------------------------------------
+# LayerNorm (+ merge gather)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("D", [128, 768, 1024])
+def test_layernorm(L, variant, D):
+    rows = 1003
+    x, w, b = rnd(rows, D, seed=50) * 3 + 0.5, rnd(D, seed=51), rnd(D, seed=52)
+    ref = torch.nn.functional.layer_norm(x, (D,), w, b, 1e-6) if variant == 0 else VO.std_layernorm(x, w, b, 1e-5)
+    out = torch.zeros((rows, D), device="cuda")
+    L.layernorm(dev(x), dev(w), dev(b), out, 1e-6 if variant == 0 else 1e-5, variant=variant)
+    check_close(out, ref, tol=2e-5, cos=0.999999, what=f"layernorm f32 v{variant} D{D}")
+    outb = torch.zeros((rows, D), dtype=torch.bfloat16, device="cuda")
+    L.layernorm(dev(x), dev(w), dev(b), outb, 1e-6 if variant == 0 else 1e-5, variant=variant)
+    assert torch.equal(outb.cpu(), out.cpu().to(torch.bfloat16)), "bf16 output must be the rounded fp32 result"
+
+
+def test_layernorm_strided_rows(L):
+    B, S, D = 5, 7, 128
+    x, w, b = rnd(B, S * D, seed=53), rnd(D, seed=54), rnd(D, seed=55)
+    out = torch.zeros((B, D), dtype=torch.bfloat16, device="cuda")
+    L.layernorm(dev(x)[:, :D], dev(w), dev(b), out, 1e-5, variant=1)
+    check_close(out, VO.std_layernorm(x[:, :D], w, b), tol=6e-3, what="layernorm strided")
+
+
+def test_layernorm_merge_gather_placement_exact(L):
+    """Merge indices are integer work: placement must be bit-exact."""
+    B, frames, nh, nw, D = 2, 2, 4, 6, 128
+    S = frames * nh * nw
+    x, w, b = rnd(B * S, D, seed=56), rnd(D, seed=57), rnd(D, seed=58)
+    plain = torch.zeros((B * S, D), device="cuda")
+    L.layernorm(dev(x), dev(w), dev(b), plain, 1e-6)
+    merged = torch.zeros((B * S // 4, 4 * D), device="cuda")
+    L.layernorm(dev(x), dev(w), dev(b), merged, 1e-6, 0, 2, nh, nw)
+    gi = VO.merge_gather_index(frames, nh, nw, 2)
+    exp = plain.cpu().view(B, S, D)[:, gi, :].reshape(B * S // 4, 4 * D)
+    assert torch.equal(merged.cpu(), exp)
+
+
+# ------------------------------------------------------------------------------------------------
+# RoPE / MRoPE
+# ------------------------------------------------------------------------------------------------
+def test_rope_apply_golden_bit_exact(L, golden_rope):
+    from llm_quest_b200.common.rope import VisionRoPE
+
+    g = golden_rope["rope2d"]
+    out = VisionRoPE.apply(dev(g["x"]), dev(g["cos"]), dev(g["sin"]))
+    assert torch.equal(out.cpu(), g["expected"]), "fp32 rotate-half must match the reference bit for bit"
+    outb = VisionRoPE.apply(dev(bf(g["x"])), dev(g["cos"]), dev(g["sin"]))
+    check_close(outb, VO.rotate_half_apply(bf(g["x"]).float(), g["cos"], g["sin"]), tol=5e-3, what="rope bf16")
+
+
+def test_rope_apply_position_ids_and_partial(L):
+    from llm_quest_b200.common.rope import RoPE
+
+    cos, sin = VO.text_rope_tables(512, 10_000, 128, 0.5)  # rot 64 of 128
+    x = rnd(2, 3, 9, 128, seed=60)
+    pid = torch.randint(0, 512, (2, 9), generator=torch.Generator().manual_seed(3))
+    out = RoPE.apply(dev(x), dev(cos), dev(sin), dev(pid))
+    assert torch.equal(out.cpu(), VO.rotate_half_apply(x, cos, sin, pid))
+
+
+def test_mrope_golden(L, golden_rope):
+    from llm_quest_b200.common.rope import RoPE
+
+    g = golden_rope["mrope"]
+    t = g["table"]
+    cos, sin = RoPE.compute_angles(t["base"], t["head_dim"], t["ctx"], rotation_factor=t["factor"])
+    oc, os_ = VO.text_rope_tables(t["ctx"], t["base"], t["head_dim"], t["factor"])
+    assert torch.equal(cos, oc) and torch.equal(sin, os_)
+    out = RoPE.apply_mrope(dev(g["x"]), dev(cos), dev(sin), dev(g["position_ids"]), g["sections"])
+    assert torch.equal(out.cpu(), g["expected"]), "fp32 MRoPE-I must match the reference bit for bit"
+    w = (1.0 + g["norm_scale"]).float()
+    outn = RoPE.apply_mrope(dev(g["x"]), dev(cos), dev(sin), dev(g["position_ids"]), g["sections"], norm_weight=dev(w))
+    check_close(outn, g["expected_norm_mrope"], tol=1e-5, cos=0.999999, what="rmsnorm+mrope f32")
+    xb = bf(g["x"])
+    outb = RoPE.apply_mrope(dev(xb), dev(cos), dev(sin), dev(g["position_ids"]), g["sections"])
+    check_close(outb, VO.mrope_apply(xb.float(), cos, sin, g["position_ids"], g["sections"]), tol=5e-3, what="mrope bf16")
+    # interleave helper (index work): exact
+    half = 32
+    c3 = cos[:, :half][g["position_ids"]]
+    s3 = sin[:, :half][g["position_ids"]]
+    mc, ms = RoPE.interleave_mrope_coeffs(c3, s3, g["sections"])
+    axes = torch.tensor(VO.mrope_slot_axes(half, g["sections"]))
+    assert torch.equal(mc, c3.permute(1, 2, 3, 0)[..., torch.arange(half), axes])
+
+
+# ------------------------------------------------------------------------------------------------
+# position ids / early fusion (bit-exact)
+# ------------------------------------------------------------------------------------------------
+def test_position_ids_goldens(L, golden_fusion):
+    for i, c in enumerate(golden_fusion["position_cases"]):
+        ids = dev(c["ids"])
+        if c["feeds"] is None:
+            feeds = torch.zeros((0, 3), dtype=torch.int64)
+            mask = torch.zeros_like(ids, dtype=torch.uint8)
+        else:
+            feeds = c["feeds"]
+            mask = None if c["mask"] is None else dev(c["mask"])
+        out = L.mrope_position_ids(ids, mask, IMG, feeds, 2)
+        assert out.dtype == torch.int64 and torch.equal(out.cpu(), c["expected"]), f"position ids case {i}"
+
+
+def test_position_ids_cfg3_full_batch(L):
+    rng = np.random.default_rng(4321)
+    rows = []
+    for _ in range(32):
+        row = []
+        for i, c in enumerate([410, 410, 410, 410, 408]):
+            row += list(rng.integers(0, 1000, size=c))
+            if i < 4:
+                row += [IMG] * 196
+        rows.append(row)
+    ids = np.array(rows, dtype=np.int64)
+    assert ids.shape == (32, 2832)
+    feeds = [[1, 28, 28]] * 4
+    exp = FO.mrope_position_ids(ids, feeds)
+    out = L.mrope_position_ids(dev(torch.from_numpy(ids)), None, IMG, torch.tensor(feeds), 2)
+    assert torch.equal(out.cpu(), torch.from_numpy(exp)) and int(out.max()) == 2103
+
+
+def test_embed_gather_scatter_goldens(L, golden_fusion):
+    for c in golden_fusion["scatter_cases"]:
+        tok = c["image_token_id"]
+        ids, table = dev(c["ids"]), dev(c["table"])
+        n_vis = c["vision"].shape[0]
+        row_map, n_ph, inv = L.fuse_scan(ids, None, tok, inv_cap=n_vis)
+        assert torch.equal(row_map.cpu(), c["row_map"])
+        assert int(n_ph.item()) == int((c["ids"] == tok).sum())
+        exp_inv = torch.full((n_vis,), -1, dtype=torch.int32)
+        sel = c["row_map"] >= 0
+        exp_inv[c["row_map"][sel].long()] = torch.arange(c["row_map"].numel(), dtype=torch.int32)[sel]
+        assert torch.equal(inv.cpu(), exp_inv)
+        for vis in (dev(c["vision"]), dev(bf(c["vision"]))):
+            out = torch.zeros(c["expected"].shape, dtype=torch.bfloat16, device="cuda")
+            L.embed_gather_scatter(ids, table, vis, row_map, out)
+            assert torch.equal(out.cpu().view(torch.uint16), c["expected"].view(torch.uint16)), "fusion must be bit-exact"
+
+
+def test_embed_gather_scatter_large_roundtrip(L):
+    """Full cfg-3 size through size-independent properties: every text row equals its table row,
+    placeholder row j equals vision row j, in flat order."""
+    b, seq, D, vocab = 32, 2832, 1024, 5000
+    g = torch.Generator().manual_seed(7)
+    ids = torch.randint(0, vocab - 1, (b, seq), generator=g)
+    tok = vocab - 1
+    for s in range(b):
+        for i in range(4):
+            st = 410 * (i + 1) + 196 * i
+            ids[s, st : st + 196] = tok
+    table = bf(torch.randn(vocab, D, generator=g))
+    n_vis = b * 4 * 196
+    vis = bf(torch.randn(n_vis, D, generator=g))
+    row_map, n_ph, inv = L.fuse_scan(dev(ids), None, tok, inv_cap=n_vis)
+    assert int(n_ph.item()) == n_vis
+    out = torch.zeros((b, seq, D), dtype=torch.bfloat16, device="cuda")
+    L.embed_gather_scatter(dev(ids), dev(table), dev(vis), row_map, out)
+    got = out.cpu().view(-1, D)
+    flat = ids.view(-1)
+    m = flat == tok
+    assert torch.equal(got[~m].view(torch.uint16), table[flat[~m]].view(torch.uint16))
+    assert torch.equal(got[m].view(torch.uint16), vis.view(torch.uint16))
+    assert torch.equal(row_map.cpu(), torch.from_numpy(FO.scatter_row_map(ids.numpy(), None, tok)))
+
+
+def test_casts(L):
+    x = rnd(100003, seed=70)
+    assert torch.equal(L.to_bf16(dev(x)).cpu(), x.to(torch.bfloat16))
+    assert torch.equal(L.to_f32(dev(bf(x))).cpu(), bf(x).float())
