@@ -130,6 +130,57 @@ def _require_cuda(*ts) -> None:
 _DT = {torch.float32: 0, torch.bfloat16: 1}
 
 
+class KernelTimer:
+    """Optional per-launch CUDA-event timing (bench.py): `with KernelTimer() as kt: ...` records an
+    event pair on the launching stream around every libvfuse launch made inside the block."""
+
+    active = None
+
+    def __init__(self):
+        self.records = []  # (kernel family, meta dict, start event, end event)
+
+    def __enter__(self):
+        KernelTimer.active = self
+        return self
+
+    def __exit__(self, *exc):
+        KernelTimer.active = None
+
+    def summary(self):
+        """{family: {"launches", "ms_total", "ms_avg", "flops", "bytes"}} — call after a synchronize."""
+        out = {}
+        for fam, meta, e0, e1 in self.records:
+            d = out.setdefault(fam, {"launches": 0, "ms_total": 0.0, "flops": 0.0, "bytes": 0.0})
+            d["launches"] += 1
+            d["ms_total"] += e0.elapsed_time(e1)
+            d["flops"] += meta.get("flops", 0.0)
+            d["bytes"] += meta.get("bytes", 0.0)
+        for d in out.values():
+            d["ms_avg"] = d["ms_total"] / d["launches"]
+        return out
+
+
+class _timed:
+    def __init__(self, family, **meta):
+        self.family, self.meta = family, meta
+        self.kt = KernelTimer.active
+
+    def __enter__(self):
+        if self.kt is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *exc):
+        if self.kt is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            self.kt.records.append((self.family, self.meta, self.e0, e1))
+
+
+_EPI_NAMES = {0: "bias_bf16", 1: "bias_f32", 2: "bias_res_f32", 3: "gelu_tanh_bf16", 4: "gelu_erf_bf16",
+              5: "qkv_rope_bf16", 6: "scatter_bf16"}
+
+
 # ------------------------------------------------------------------------------------------------
 # tensor-level wrappers
 # ------------------------------------------------------------------------------------------------
@@ -158,8 +209,9 @@ def gemm(a, w, mode, out, bias=None, res=None, rope=None, dst_rows=None, grp_row
     ep.dst_rows = _p(dst_rows)
     if bias is not None:
         assert bias.dtype == torch.float32 and bias.is_contiguous() and bias.numel() == N
-    check(lib().vf_gemm_bf16(a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), M, N, K, C.byref(ep), _stream()),
-          "vf_gemm_bf16")
+    with _timed("gemm_" + _EPI_NAMES.get(mode, str(mode)), flops=2.0 * M * N * K):
+        check(lib().vf_gemm_bf16(a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), M, N, K, C.byref(ep),
+                                 _stream()), "vf_gemm_bf16")
     return out
 
 
@@ -169,12 +221,13 @@ def patch_embed(pixels, weight2d, bias, pos, out, P, tp, out_rows_per_sample, ou
     assert pixels.dtype == torch.bfloat16 and pixels.is_contiguous() and pixels.dim() == 5
     B, Cc, T, H, W = pixels.shape
     N = weight2d.shape[0]
-    check(
-        lib().vf_patch_embed(pixels.data_ptr(), B, Cc, T, H, W, P, tp, weight2d.data_ptr(), _p(bias), _p(pos),
-                             pos.stride(0) if pos is not None else 0, N, out.data_ptr(), out.stride(-2),
-                             out_rows_per_sample, out_row_off, _stream()),
-        "vf_patch_embed",
-    )
+    with _timed("patch_embed", flops=2.0 * B * (T // tp) * (H // P) * (W // P) * N * weight2d.shape[1]):
+        check(
+            lib().vf_patch_embed(pixels.data_ptr(), B, Cc, T, H, W, P, tp, weight2d.data_ptr(), _p(bias), _p(pos),
+                                 pos.stride(0) if pos is not None else 0, N, out.data_ptr(), out.stride(-2),
+                                 out_rows_per_sample, out_row_off, _stream()),
+            "vf_patch_embed",
+        )
     return out
 
 
@@ -182,7 +235,9 @@ def attention(qkv, out, B, S, H, scale):
     _require_cuda(qkv, out)
     assert qkv.dtype == torch.bfloat16 and qkv.is_contiguous() and out.dtype == torch.bfloat16 and out.is_contiguous()
     assert qkv.numel() == B * S * 3 * H * 64 and out.numel() == B * S * H * 64
-    check(lib().vf_attention_fwd(qkv.data_ptr(), out.data_ptr(), B, S, H, float(scale), _stream()), "vf_attention_fwd")
+    with _timed("attention", flops=4.0 * B * H * S * S * 64):
+        check(lib().vf_attention_fwd(qkv.data_ptr(), out.data_ptr(), B, S, H, float(scale), _stream()),
+              "vf_attention_fwd")
     return out
 
 
@@ -190,11 +245,12 @@ def layernorm(x2d, w, b, out, eps, variant=0, merge=1, nh=0, nw=0):
     _require_cuda(x2d, w, b, out)
     rows, D = x2d.shape
     assert x2d.stride(1) == 1 and out.is_contiguous()
-    check(
-        lib().vf_layernorm(x2d.data_ptr(), _DT[x2d.dtype], x2d.stride(0), w.data_ptr(), b.data_ptr(), out.data_ptr(),
-                           _DT[out.dtype], rows, D, float(eps), variant, merge, nh, nw, _stream()),
-        "vf_layernorm",
-    )
+    with _timed("layernorm", bytes=float(rows * D * (x2d.element_size() + out.element_size()))):
+        check(
+            lib().vf_layernorm(x2d.data_ptr(), _DT[x2d.dtype], x2d.stride(0), w.data_ptr(), b.data_ptr(),
+                               out.data_ptr(), _DT[out.dtype], rows, D, float(eps), variant, merge, nh, nw, _stream()),
+            "vf_layernorm",
+        )
     return out
 
 

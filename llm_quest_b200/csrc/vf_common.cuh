@@ -306,6 +306,19 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   return d;
 }
 
+// 32-byte-swizzle K-major operand (rows 32 B = 16 bf16 wide, 8-row groups `sbo_bytes` apart): the
+// layout TMA produces with CU_TENSOR_MAP_SWIZZLE_32B and a 32-byte inner box. One descriptor covers
+// exactly one K=16 MMA slice. layout code 6 = SWIZZLE_32B.
+__device__ __forceinline__ uint64_t umma_desc_sw32(uint32_t smem_addr, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(6) << 61;
+  return d;
+}
+
 // Instruction descriptor, kind::f16, bf16 x bf16 -> fp32, dense.
 // bits: [4,6) D fmt (1=f32) | [7,10) A fmt (1=bf16) | [10,13) B fmt | 15 A major | 16 B major |
 //       [17,23) N>>3 | [24,29) M>>4

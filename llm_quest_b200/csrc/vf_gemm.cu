@@ -14,7 +14,11 @@
 //     residual add, axial RoPE (pairs i / i+32 of a head live in the same thread) and the row
 //     remaps are all register-local.
 //   * patch-embedding mode gathers the A tile with ONE 5-D TMA box per stage straight from the
-//     [B,C,T,H,W] pixel tensor (im2col-free): tile rows are a PH x PW rectangle of patches.
+//     [B,C,T,H,W] pixel tensor (im2col-free): tile rows are a 16 x 8 rectangle of patches. A patch
+//     row is only 32 B wide, and TMA pads narrower-than-span rows under the 128 B swizzle (measured:
+//     scratch/tma_probe.cu), so this operand uses the 32 B swizzle instead: the box lands as
+//     [ph 16][py 4][pw 8][16 px], i.e. for every K=16 slice (one pixel row py) a dense K-major
+//     SW32 tile whose 8-row groups (one patch row ph) are 1024 B apart.
 #include "vf_common.cuh"
 #include "../../include/vfuse.h"
 
@@ -43,6 +47,7 @@ struct GemmParams {
   int rope_period;
   int rope_cols;
   const int* dst_rows;
+  int vec_ok;          // out (and res) rows are 16-byte aligned: 128-bit stores allowed
   // patch-embedding mode
   int patch;
   int PW, PH;          // tile rectangle in patches (PW*PH == 128)
@@ -151,7 +156,7 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
             const int plane = kb / kb_per_plane;              // c*tp + dt
             const int py0 = (kb % kb_per_plane) * rows_per_kb;
             const int c = plane / p.tp, dt = plane % p.tp;
-            tma_load_5d(a_dst, &tmA, &full_bar[stage], 0, py0, pc2, pc3, pimg + c * p.T + dt);
+            tma_load_5d(a_dst, &tmA, &full_bar[stage], 0, pc2, py0, pc3, pimg + c * p.T + dt);
           } else {
             tma_load_2d(a_dst, &tmA, &full_bar[stage], kb * BK, m_blk * BM);
           }
@@ -178,10 +183,16 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
           const uint32_t a_addr = smem_u32(smem + stage * L::STAGE_BYTES);
           const uint64_t a_desc = umma_desc_sw128(a_addr);
           const uint64_t b_desc = umma_desc_sw128(a_addr + L::A_BYTES);
+          if (p.patch) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            // advance 16 bf16 = 32 B inside the 128 B swizzle atom: +2 in the (addr>>4) field
-            umma_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+            for (int k = 0; k < BK / 16; ++k)  // slice k = pixel row py0+k: [16 ph][8 pw][32 B], SBO 1024 B
+              umma_ss(d_tmem, umma_desc_sw32(a_addr + k * 256, 1024), b_desc + 2 * k, idesc, (kb | k) != 0);
+          } else {
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) {
+              // advance 16 bf16 = 32 B inside the 128 B swizzle atom: +2 in the (addr>>4) field
+              umma_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+            }
           }
           umma_commit(&empty_bar[stage]);  // smem slot is free once these MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -301,18 +312,18 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
           tmem_ld_wait();
           const int cbase = col0 + c * 32;
           if (!row_ok || cbase >= p.N) continue;
-          const bool full = (cbase + 32 <= p.N);
+          const bool full = (cbase + 32 <= p.N) && p.vec_ok;
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             float x = __uint_as_float(r[j]);
-            if (p.bias && (full || cbase + j < p.N)) x += __ldg(p.bias + cbase + j);
+            if (p.bias && cbase + j < p.N) x += __ldg(p.bias + cbase + j);
             v[j] = x;
           }
           if (pos_row) {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              if (full || cbase + j < p.N) v[j] += __ldg(pos_row + cbase + j);
+              if (cbase + j < p.N) v[j] += __ldg(pos_row + cbase + j);
           }
           if constexpr (EPI == VF_EPI_BIAS_RES_F32) {
             const float* rrow = p.res + out_row * p.ldr + cbase;
@@ -436,11 +447,15 @@ extern "C" int vf_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t l
   VF_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0,
              VF_ERR_ALIGN, "vf_gemm_bf16: A/W must be 16-byte aligned");
   const bool out_f32 = ep->mode == VF_EPI_BIAS_F32 || ep->mode == VF_EPI_BIAS_RES_F32;
-  VF_REQUIRE((reinterpret_cast<uintptr_t>(ep->out) & 15) == 0 && (ep->ldo % (out_f32 ? 4 : 8)) == 0,
-             VF_ERR_ALIGN, "vf_gemm_bf16: out must be 16-byte aligned with a 16-byte multiple pitch");
-  if (ep->mode == VF_EPI_BIAS_RES_F32)
-    VF_REQUIRE(ep->res && (reinterpret_cast<uintptr_t>(ep->res) & 15) == 0 && (ep->ldr % 4) == 0,
-               VF_ERR_ARG, "vf_gemm_bf16: residual pointer missing or misaligned");
+  VF_REQUIRE(ep->ldo >= N, VF_ERR_ARG, "vf_gemm_bf16: ldo smaller than N");
+  // 128-bit stores need 16-byte aligned rows; otherwise (e.g. a 10-class head) fall back to scalar stores
+  bool vec_ok = (reinterpret_cast<uintptr_t>(ep->out) & 15) == 0 && (ep->ldo % (out_f32 ? 4 : 8)) == 0;
+  if (ep->mode == VF_EPI_BIAS_RES_F32) {
+    VF_REQUIRE(ep->res, VF_ERR_ARG, "vf_gemm_bf16: residual pointer missing");
+    vec_ok = vec_ok && (reinterpret_cast<uintptr_t>(ep->res) & 15) == 0 && (ep->ldr % 4) == 0;
+  }
+  if (ep->mode == VF_EPI_QKV_ROPE_BF16)
+    VF_REQUIRE(vec_ok, VF_ERR_ALIGN, "vf_gemm_bf16: the QKV+RoPE epilogue needs 16-byte aligned output rows");
   if (ep->mode == VF_EPI_QKV_ROPE_BF16)
     VF_REQUIRE(ep->rope_cos && ep->rope_sin && ep->rope_period > 0 && (ep->rope_cols % 64) == 0 &&
                    (N % 64) == 0,
@@ -461,6 +476,7 @@ extern "C" int vf_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t l
   p.rope_cos = ep->rope_cos; p.rope_sin = ep->rope_sin;
   p.rope_period = ep->rope_period; p.rope_cols = ep->rope_cols;
   p.dst_rows = ep->dst_rows;
+  p.vec_ok = vec_ok ? 1 : 0;
 
   CUtensorMap tmA, tmB;
   {
@@ -491,8 +507,8 @@ extern "C" int vf_patch_embed(const void* pixels, int32_t B, int32_t C, int32_t 
                               int64_t out_row_off, void* stream) {
   VF_REQUIRE(pixels && weight && out, VF_ERR_ARG, "vf_patch_embed: null pointer");
   VF_REQUIRE(B > 0 && C > 0 && T > 0 && H > 0 && W > 0 && N > 0, VF_ERR_ARG, "vf_patch_embed: bad shape");
-  VF_REQUIRE(P == 8 || P == 16 || P == 32, VF_ERR_ARG,
-             "vf_patch_embed: patch size %d unsupported (TMA path needs 8, 16 or 32)", P);
+  VF_REQUIRE(P == 16, VF_ERR_ARG,
+             "vf_patch_embed: patch size %d unsupported (the TMA gather is built for 16x16 patches)", P);
   VF_REQUIRE(tp >= 1 && T % tp == 0 && H % P == 0 && W % P == 0, VF_ERR_ARG,
              "vf_patch_embed: T/H/W not divisible by the patch shape");
   VF_REQUIRE((W % 8) == 0, VF_ERR_ALIGN, "vf_patch_embed: image width must be a multiple of 8 pixels");
@@ -503,15 +519,8 @@ extern "C" int vf_patch_embed(const void* pixels, int32_t B, int32_t C, int32_t 
   VF_REQUIRE(K % BK == 0, VF_ERR_ARG, "vf_patch_embed: C*tp*P*P must be a multiple of 64");
   const int nh = H / P, nw = W / P, Tp = T / tp;
 
-  // tile rectangle: PW = smallest of {4,8,16,32} that wastes the least of the frame width
-  int best_pw = 32;
-  double best_eff = -1.0;
-  for (int pw = 4; pw <= 32; pw *= 2) {
-    const int ph = BM / pw;
-    const int nb_w = (nw + pw - 1) / pw, nb_h = (nh + ph - 1) / ph;
-    const double eff = double(nw) * nh / (double(nb_w) * pw * nb_h * ph);
-    if (eff > best_eff + 1e-9) { best_eff = eff; best_pw = pw; }
-  }
+  // tile rectangle: 16 patch rows x 8 patch columns (see the SW32 layout note at the top)
+  const int best_pw = 8;
   GemmParams p{};
   p.patch = 1;
   p.PW = best_pw; p.PH = BM / best_pw;
@@ -528,15 +537,16 @@ extern "C" int vf_patch_embed(const void* pixels, int32_t B, int32_t C, int32_t 
   p.bias = bias;
   p.out = out; p.ldo = ldo;
   p.grp_stride = out_rows_per_sample; p.row_off = out_row_off;
+  p.vec_ok = 1;
 
   CUtensorMap tmA, tmB;
   {
-    // dims (fastest first): px[P], py[P], pw[nw], ph[nh], image plane [B*C*T]
-    uint64_t dims[5] = {(uint64_t)P, (uint64_t)P, (uint64_t)nw, (uint64_t)nh, (uint64_t)B * C * T};
-    uint64_t strides[4] = {(uint64_t)W * 2, (uint64_t)P * 2, (uint64_t)W * P * 2, (uint64_t)H * W * 2};
-    uint32_t box[5] = {(uint32_t)P, (uint32_t)(BK / P), (uint32_t)p.PW, (uint32_t)p.PH, 1};
+    // dims (fastest first): px[P], pw[nw], py[P], ph[nh], image plane [B*C*T]
+    uint64_t dims[5] = {(uint64_t)P, (uint64_t)nw, (uint64_t)P, (uint64_t)nh, (uint64_t)B * C * T};
+    uint64_t strides[4] = {(uint64_t)P * 2, (uint64_t)W * 2, (uint64_t)W * P * 2, (uint64_t)H * W * 2};
+    uint32_t box[5] = {(uint32_t)P, (uint32_t)p.PW, (uint32_t)(BK / P), (uint32_t)p.PH, 1};
     int e = encode_tmap(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, pixels, dims, strides, box,
-                        CU_TENSOR_MAP_SWIZZLE_128B);
+                        CU_TENSOR_MAP_SWIZZLE_32B);
     if (e) return e;
   }
   {

@@ -47,7 +47,9 @@ class _Packed:
         self._store = {}
 
     def get(self, key, params, build):
-        sig = tuple((p.data_ptr(), p._version, p.device, p.dtype) for p in params if p is not None)
+        # inference tensors carry no version counter (and cannot be modified in place anyway)
+        sig = tuple((p.data_ptr(), 0 if p.is_inference() else p._version, p.device, p.dtype)
+                    for p in params if p is not None)
         hit = self._store.get(key)
         if hit is not None and hit[0] == sig:
             return hit[1]
