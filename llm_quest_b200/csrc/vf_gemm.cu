@@ -64,7 +64,8 @@ struct SmemLayout {
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
-  static constexpr int TOTAL = BAR_OFF + 256 + 1024;  // barriers + alignment slack
+  static constexpr int EPI_OFF = BAR_OFF + 256;            // 4 epilogue warps x 2 staging blocks of 32x32 fp32
+  static constexpr int TOTAL = EPI_OFF + 4 * 8192 + 1024;  // + alignment slack
 };
 
 __device__ __forceinline__ void wait_or_trap(uint64_t* bar, uint32_t parity) {
@@ -203,172 +204,210 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
     }
   } else {
     // ------------------------------------------------------------------ epilogue (warps 2..5)
+    // tcgen05.ld hands every thread one accumulator ROW; global memory wants warps to touch whole
+    // 128-byte lines. Each warp therefore transposes 32x32 fp32 blocks through a private, XOR-swizzled
+    // (conflict-free) shared-memory buffer and does all epilogue math + I/O in the coalesced mapping:
+    // lane l owns columns 4*(l%8)..+3 of rows (l/8)+4i, i = 0..7.
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    float* stA = reinterpret_cast<float*>(smem + L::EPI_OFF + (warp - 2) * 8192);
+    float* stB = stA + 1024;
+    const int cl = lane & 7;       // 16-byte column group inside a 32-column block
+    const int rl = lane >> 3;      // row offset inside a group of 4 rows
     int acc = 0;
     uint32_t acc_phase = 0;
+
+    // write this thread's accumulator row (32 fp32) into the staging block, chunk j -> slot j ^ (row & 7)
+    auto stage_row = [&](float* st, const uint32_t* r) {
+      float4* row = reinterpret_cast<float4*>(st + lane * 32);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        row[j ^ (lane & 7)] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                          __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+    };
+    auto read_staged = [&](const float* st, int rr) {
+      return reinterpret_cast<const float4*>(st + rr * 32)[cl ^ (rr & 7)];
+    };
+
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int n_blk = tile % p.num_n_blk;
       const int m_blk = tile / p.num_n_blk;
-      const int r_local = quarter * 32 + lane;
+      const int col0 = n_blk * BN;
 
-      // ---- which output row does this thread own?
-      bool row_ok;
-      long long out_row;
-      const float* pos_row = nullptr;
-      if (p.patch) {
-        int t = m_blk;
-        const int pwb = t % p.n_pwb; t /= p.n_pwb;
-        const int phb = t % p.n_phb; t /= p.n_phb;
-        const int tpr = t % p.Tp;
-        const int b = t / p.Tp;
-        const int ph = phb * p.PH + r_local / p.PW;
-        const int pw = pwb * p.PW + r_local % p.PW;
-        row_ok = (ph < p.nh) && (pw < p.nw);
-        const int sp = ph * p.nw + pw;
-        out_row = (long long)b * p.grp_stride + p.row_off + (long long)tpr * p.nh * p.nw + sp;
-        if (p.pos) pos_row = p.pos + (long long)sp * p.ld_pos;
-      } else {
-        const int m = m_blk * BM + r_local;
-        row_ok = m < p.M;
-        if (EPI == VF_EPI_SCATTER_BF16) {
-          const int d = row_ok ? p.dst_rows[m] : -1;
-          row_ok = d >= 0;
-          out_row = d;
-        } else if (p.grp_rows > 0) {
-          out_row = (long long)(m / p.grp_rows) * p.grp_stride + (m % p.grp_rows) + p.row_off;
+      // ---- output row (element offset / validity) of the 8 rows this lane touches
+      long long orow[8];
+      int aux[8];  // patch: spatial index (pos row); rope: table row; otherwise unused
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r_local = quarter * 32 + rl + 4 * i;
+        long long o = -1;
+        int ax = 0;
+        if (p.patch) {
+          int t = m_blk;
+          const int pwb = t % p.n_pwb; t /= p.n_pwb;
+          const int phb = t % p.n_phb; t /= p.n_phb;
+          const int tpr = t % p.Tp;
+          const int b = t / p.Tp;
+          const int ph = phb * p.PH + r_local / p.PW;
+          const int pw = pwb * p.PW + r_local % p.PW;
+          if (ph < p.nh && pw < p.nw) {
+            ax = ph * p.nw + pw;
+            o = (long long)b * p.grp_stride + p.row_off + (long long)tpr * p.nh * p.nw + ax;
+          }
         } else {
-          out_row = m;
+          const int m = m_blk * BM + r_local;
+          if (m < p.M) {
+            if (EPI == VF_EPI_SCATTER_BF16) o = p.dst_rows[m];
+            else if (p.grp_rows > 0) o = (long long)(m / p.grp_rows) * p.grp_stride + (m % p.grp_rows) + p.row_off;
+            else o = m;
+            if (EPI == VF_EPI_QKV_ROPE_BF16) ax = m % p.rope_period;
+          }
         }
+        orow[i] = o;
+        aux[i] = ax;
       }
 
       wait_or_trap(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
-      const int col0 = n_blk * BN;
 
       if constexpr (EPI == VF_EPI_QKV_ROPE_BF16) {
-        const int m = m_blk * BM + r_local;
-        const int prow = m % p.rope_period;
-        const float4* cs = reinterpret_cast<const float4*>(p.rope_cos + (long long)prow * 32);
-        const float4* sn = reinterpret_cast<const float4*>(p.rope_sin + (long long)prow * 32);
-        __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) + out_row * p.ldo;
+        __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(p.out);
 #pragma unroll 1
         for (int h = 0; h < BN / 64; ++h) {
+          const int hc = col0 + h * 64;          // first column of this head
+          uint32_t r1[32], r2[32];
+          tmem_ld_x32(t_row + h * 64, r1);
+          tmem_ld_x32(t_row + h * 64 + 32, r2);
+          tmem_ld_wait();
+          __syncwarp();                          // previous head fully consumed by all lanes
+          stage_row(stA, r1);
+          stage_row(stB, r2);
           __syncwarp();
-          const int hc = col0 + h * 64;
+          if (hc >= p.N) continue;
           const bool rot = hc < p.rope_cols;
+          float4 b1 = make_float4(0.f, 0.f, 0.f, 0.f), b2 = b1;
+          if (p.bias) {
+            b1 = __ldg(reinterpret_cast<const float4*>(p.bias + hc) + cl);
+            b2 = __ldg(reinterpret_cast<const float4*>(p.bias + hc + 32) + cl);
+          }
+          // all table loads first (independent), then math, then predicated stores: no branches in the
+          // unrolled body, so the 8 rows of this lane overlap their latencies
+          float4 cv[8], sv[8];
+          if (rot) {
 #pragma unroll
-          for (int sub = 0; sub < 2; ++sub) {  // 16 pairs at a time
-            uint32_t x1[16], x2[16];
-            tmem_ld_x16(t_row + h * 64 + sub * 16, x1);
-            tmem_ld_x16(t_row + h * 64 + 32 + sub * 16, x2);
-            tmem_ld_wait();
-            uint32_t o1[8], o2[8];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              float a[4], b[4];
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const int j = q * 4 + e;
-                const int c1 = hc + sub * 16 + j;
-                a[e] = __uint_as_float(x1[j]) + (p.bias && c1 < p.N ? p.bias[c1] : 0.f);
-                b[e] = __uint_as_float(x2[j]) + (p.bias && c1 + 32 < p.N ? p.bias[c1 + 32] : 0.f);
-              }
-              if (rot && row_ok) {
-                const float4 c4 = cs[sub * 4 + q];
-                const float4 s4 = sn[sub * 4 + q];
-                const float cc[4] = {c4.x, c4.y, c4.z, c4.w};
-                const float ss[4] = {s4.x, s4.y, s4.z, s4.w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const float ra = a[e] * cc[e] - b[e] * ss[e];
-                  const float rb = b[e] * cc[e] + a[e] * ss[e];
-                  a[e] = ra;
-                  b[e] = rb;
-                }
-              }
-              o1[q * 2 + 0] = pack_bf16(a[0], a[1]);
-              o1[q * 2 + 1] = pack_bf16(a[2], a[3]);
-              o2[q * 2 + 0] = pack_bf16(b[0], b[1]);
-              o2[q * 2 + 1] = pack_bf16(b[2], b[3]);
+            for (int i = 0; i < 8; ++i) {
+              cv[i] = __ldg(reinterpret_cast<const float4*>(p.rope_cos + (long long)aux[i] * 32) + cl);
+              sv[i] = __ldg(reinterpret_cast<const float4*>(p.rope_sin + (long long)aux[i] * 32) + cl);
             }
-            if (row_ok && hc + 64 <= p.N) {
-              uint4* d1 = reinterpret_cast<uint4*>(orow + hc + sub * 16);
-              uint4* d2 = reinterpret_cast<uint4*>(orow + hc + 32 + sub * 16);
-              d1[0] = make_uint4(o1[0], o1[1], o1[2], o1[3]);
-              d1[1] = make_uint4(o1[4], o1[5], o1[6], o1[7]);
-              d2[0] = make_uint4(o2[0], o2[1], o2[2], o2[3]);
-              d2[1] = make_uint4(o2[4], o2[5], o2[6], o2[7]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              cv[i] = make_float4(1.f, 1.f, 1.f, 1.f);
+              sv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rr = rl + 4 * i;
+            float4 x1 = read_staged(stA, rr), x2 = read_staged(stB, rr);
+            x1.x += b1.x; x1.y += b1.y; x1.z += b1.z; x1.w += b1.w;
+            x2.x += b2.x; x2.y += b2.y; x2.z += b2.z; x2.w += b2.w;
+            const float4 c = cv[i], sn = sv[i];
+            float4 y1, y2;
+            y1.x = x1.x * c.x - x2.x * sn.x; y2.x = x2.x * c.x + x1.x * sn.x;
+            y1.y = x1.y * c.y - x2.y * sn.y; y2.y = x2.y * c.y + x1.y * sn.y;
+            y1.z = x1.z * c.z - x2.z * sn.z; y2.z = x2.z * c.z + x1.z * sn.z;
+            y1.w = x1.w * c.w - x2.w * sn.w; y2.w = x2.w * c.w + x1.w * sn.w;
+            if (orow[i] >= 0) {
+              __nv_bfloat16* o = outp + orow[i] * p.ldo + hc + cl * 4;
+              *reinterpret_cast<uint2*>(o) = make_uint2(pack_bf16(y1.x, y1.y), pack_bf16(y1.z, y1.w));
+              *reinterpret_cast<uint2*>(o + 32) = make_uint2(pack_bf16(y2.x, y2.y), pack_bf16(y2.z, y2.w));
             }
           }
         }
       } else {
         constexpr bool OUT_F32 = (EPI == VF_EPI_BIAS_F32 || EPI == VF_EPI_BIAS_RES_F32);
+        uint32_t r[32];
+        tmem_ld_x32(t_row, r);
 #pragma unroll 1
         for (int c = 0; c < BN / 32; ++c) {
-          __syncwarp();
-          uint32_t r[32];
-          tmem_ld_x32(t_row + c * 32, r);
           tmem_ld_wait();
+          __syncwarp();                          // previous block fully consumed by all lanes
+          stage_row(stA, r);
+          if (c + 1 < BN / 32) tmem_ld_x32(t_row + (c + 1) * 32, r);  // overlaps the math below
+          __syncwarp();
           const int cbase = col0 + c * 32;
-          if (!row_ok || cbase >= p.N) continue;
-          const bool full = (cbase + 32 <= p.N) && p.vec_ok;
-          float v[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float x = __uint_as_float(r[j]);
-            if (p.bias && cbase + j < p.N) x += __ldg(p.bias + cbase + j);
-            v[j] = x;
+          const int cc = cbase + cl * 4;         // first of this lane's 4 columns
+          if (cc >= p.N) continue;
+          const bool vec = p.vec_ok && (cc + 4 <= p.N);
+          float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.bias) {
+            if (cc + 4 <= p.N) bv = __ldg(reinterpret_cast<const float4*>(p.bias + cc));
+            else {
+              bv.x = p.bias[cc];
+              if (cc + 1 < p.N) bv.y = p.bias[cc + 1];
+              if (cc + 2 < p.N) bv.z = p.bias[cc + 2];
+            }
           }
-          if (pos_row) {
+          // residual / pos-embed rows are fetched for all 8 rows up front (they may alias `out`, so the
+          // compiler cannot hoist them across the stores itself); rows that are masked out read row 0
+          float4 ex[8];
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (cbase + j < p.N) v[j] += __ldg(pos_row + cbase + j);
-          }
+          for (int i = 0; i < 8; ++i) ex[i] = make_float4(0.f, 0.f, 0.f, 0.f);
           if constexpr (EPI == VF_EPI_BIAS_RES_F32) {
-            const float* rrow = p.res + out_row * p.ldr + cbase;
-            if (full) {
+            if (vec) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float4 t4 = reinterpret_cast<const float4*>(rrow)[j];
-                v[j * 4 + 0] += t4.x; v[j * 4 + 1] += t4.y; v[j * 4 + 2] += t4.z; v[j * 4 + 3] += t4.w;
+              for (int i = 0; i < 8; ++i)
+                ex[i] = *reinterpret_cast<const float4*>(p.res + (orow[i] < 0 ? 0 : orow[i]) * p.ldr + cc);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float* rp = p.res + (orow[i] < 0 ? 0 : orow[i]) * p.ldr + cc;
+                ex[i].x = rp[0];
+                if (cc + 1 < p.N) ex[i].y = rp[1];
+                if (cc + 2 < p.N) ex[i].z = rp[2];
+                if (cc + 3 < p.N) ex[i].w = rp[3];
               }
-            } else {
-              for (int j = 0; j < 32; ++j) if (cbase + j < p.N) v[j] += rrow[j];
             }
           }
-          if constexpr (EPI == VF_EPI_GELU_TANH_BF16) {
+          if (p.patch && p.pos) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = gelu_tanh_f(v[j]);
+            for (int i = 0; i < 8; ++i)
+              ex[i] = __ldg(reinterpret_cast<const float4*>(p.pos + (long long)aux[i] * p.ld_pos + cc));
           }
-          if constexpr (EPI == VF_EPI_GELU_ERF_BF16) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = gelu_erf_f(v[j]);
-          }
-          if constexpr (OUT_F32) {
-            float* orow = reinterpret_cast<float*>(p.out) + out_row * p.ldo + cbase;
-            if (full) {
+          for (int i = 0; i < 8; ++i) {
+            const float4 x = read_staged(stA, rl + 4 * i);
+            float v[4] = {x.x + bv.x + ex[i].x, x.y + bv.y + ex[i].y, x.z + bv.z + ex[i].z, x.w + bv.w + ex[i].w};
+            if constexpr (EPI == VF_EPI_GELU_TANH_BF16) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j)
-                reinterpret_cast<float4*>(orow)[j] = make_float4(v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]);
-            } else {
-              for (int j = 0; j < 32; ++j) if (cbase + j < p.N) orow[j] = v[j];
+              for (int e = 0; e < 4; ++e) v[e] = gelu_tanh_f(v[e]);
             }
-          } else {
-            __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) + out_row * p.ldo + cbase;
-            if (full) {
+            if constexpr (EPI == VF_EPI_GELU_ERF_BF16) {
 #pragma unroll
-              for (int j = 0; j < 4; ++j)
-                reinterpret_cast<uint4*>(orow)[j] =
-                    make_uint4(pack_bf16(v[j * 8 + 0], v[j * 8 + 1]), pack_bf16(v[j * 8 + 2], v[j * 8 + 3]),
-                               pack_bf16(v[j * 8 + 4], v[j * 8 + 5]), pack_bf16(v[j * 8 + 6], v[j * 8 + 7]));
-            } else {
-              for (int j = 0; j < 32; ++j) if (cbase + j < p.N) orow[j] = __float2bfloat16_rn(v[j]);
+              for (int e = 0; e < 4; ++e) v[e] = gelu_erf_f(v[e]);
+            }
+            if (orow[i] >= 0) {
+              if constexpr (OUT_F32) {
+                float* o = reinterpret_cast<float*>(p.out) + orow[i] * p.ldo + cc;
+                if (vec) *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+                else {
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) if (cc + e < p.N) o[e] = v[e];
+                }
+              } else {
+                __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + orow[i] * p.ldo + cc;
+                if (vec) *reinterpret_cast<uint2*>(o) = make_uint2(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]));
+                else {
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) if (cc + e < p.N) o[e] = __float2bfloat16_rn(v[e]);
+                }
+              }
             }
           }
         }
       }
-      // release the accumulator buffer
+      // release the accumulator buffer (all tcgen05.ld of this warp have completed)
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
@@ -448,6 +487,7 @@ extern "C" int vf_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t l
              VF_ERR_ALIGN, "vf_gemm_bf16: A/W must be 16-byte aligned");
   const bool out_f32 = ep->mode == VF_EPI_BIAS_F32 || ep->mode == VF_EPI_BIAS_RES_F32;
   VF_REQUIRE(ep->ldo >= N, VF_ERR_ARG, "vf_gemm_bf16: ldo smaller than N");
+  VF_REQUIRE((reinterpret_cast<uintptr_t>(ep->bias) & 15) == 0, VF_ERR_ALIGN, "vf_gemm_bf16: bias must be 16-byte aligned");
   // 128-bit stores need 16-byte aligned rows; otherwise (e.g. a 10-class head) fall back to scalar stores
   bool vec_ok = (reinterpret_cast<uintptr_t>(ep->out) & 15) == 0 && (ep->ldo % (out_f32 ? 4 : 8)) == 0;
   if (ep->mode == VF_EPI_BIAS_RES_F32) {
@@ -515,6 +555,9 @@ extern "C" int vf_patch_embed(const void* pixels, int32_t B, int32_t C, int32_t 
   VF_REQUIRE((reinterpret_cast<uintptr_t>(pixels) & 15) == 0 && (reinterpret_cast<uintptr_t>(weight) & 15) == 0 &&
                  (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (ldo % 4) == 0,
              VF_ERR_ALIGN, "vf_patch_embed: pointers must be 16-byte aligned");
+  VF_REQUIRE((reinterpret_cast<uintptr_t>(bias) & 15) == 0 && (reinterpret_cast<uintptr_t>(pos) & 15) == 0 &&
+                 (ld_pos % 4) == 0 && (N % 4) == 0,
+             VF_ERR_ALIGN, "vf_patch_embed: bias/pos must be 16-byte aligned, ld_pos and N multiples of 4");
   const int K = C * tp * P * P;
   VF_REQUIRE(K % BK == 0, VF_ERR_ARG, "vf_patch_embed: C*tp*P*P must be a multiple of 64");
   const int nh = H / P, nw = W / P, Tp = T / tp;

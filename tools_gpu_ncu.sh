@@ -1,0 +1,24 @@
+#!/bin/bash
+# ncu evidence: (1) launch list with device time per launch, (2) full capture of the dominant kernels
+mkdir -p gpurun_out
+cat > /tmp/one_step.py <<'PY'
+import sys, torch
+sys.path.insert(0, '.')
+import bench
+from llm_quest_b200.qwen.qwen3_5.qwen3_5_vision_model import Qwen3_5VisionModel
+torch.manual_seed(123)
+m = Qwen3_5VisionModel(bench.qwen_cfg(448)).eval().cuda()
+x = torch.randn(64, 3, 2, 448, 448).to(torch.bfloat16).cuda()
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 2
+with torch.inference_mode():
+    for _ in range(n):
+        m(x)
+torch.cuda.synchronize()
+PY
+ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv python /tmp/one_step.py 2 > gpurun_out/ncu_list.log 2>&1
+echo "list exit=$?"
+ncu --set full --clock-control none --import-source on -k regex:gemm_kernel -s 54 -c 8 -o gpurun_out/prof_gemm -f python /tmp/one_step.py 2 > gpurun_out/ncu_gemm.log 2>&1
+echo "gemm exit=$?"
+ncu --set full --clock-control none --import-source on -k regex:attention_kernel -s 12 -c 1 -o gpurun_out/prof_attn -f python /tmp/one_step.py 2 > gpurun_out/ncu_attn.log 2>&1
+echo "attn exit=$?"
+ls -la gpurun_out/*.ncu-rep
