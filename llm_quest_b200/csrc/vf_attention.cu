@@ -138,82 +138,95 @@ attention_kernel(const AttnParams p, const __grid_constant__ CUtensorMap tmQKV) 
       }
     }
     } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+      // ---------------------------------------------------------------- MMA issuer
+      // The whole warp walks the (warp-uniform) schedule so that addresses and descriptors live in
+      // uniform registers; one elected lane issues the tcgen05 instructions.
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);  // Q K^T : both K-major
       constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);   // P V   : V is MN-major
-      const uint32_t q_addr = smem_u32(smem + AttnSmem::Q_OFF);
-      const uint32_t k_addr = smem_u32(smem + AttnSmem::K_OFF);
-      const uint32_t v_addr = smem_u32(smem + AttnSmem::V_OFF);
+      const uint64_t q_desc = umma_desc_sw128(smem_u32(smem + AttnSmem::Q_OFF));
+      const uint64_t k_desc = umma_desc_sw128(smem_u32(smem + AttnSmem::K_OFF));
+      const uint64_t v_desc = umma_desc_sw128(smem_u32(smem + AttnSmem::V_OFF));
+      constexpr uint64_t TILE_DESC = TILE_BYTES >> 4;   // one 16 KB tile further, in descriptor units
       int ks = 0, vs = 0;
       uint32_t kph = 0, vph = 0, qph = 0;
-      uint32_t pph[2] = {0, 0};
-      uint32_t oeph[2] = {0, 0};
+      uint32_t pph0 = 0, pph1 = 0, oeph0 = 0, oeph1 = 0;
 
-      auto issue_s = [&](int t, int kstage) {
-        const uint64_t a = umma_desc_sw128(q_addr + t * TILE_BYTES);
-        const uint64_t bdesc = umma_desc_sw128(k_addr + kstage * TILE_BYTES);
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_ss(tmem_base + t * 128, a + 2 * k, bdesc + 2 * k, idesc_s, k != 0);
-        umma_commit(&s_full[t]);
-      };
-      auto issue_pv = [&](int t, int vstage, bool accumulate) {
-        const uint64_t bdesc = umma_desc_sw128(v_addr + vstage * TILE_BYTES);
-#pragma unroll
-        for (int k = 0; k < 8; ++k)  // 16 keys per MMA: 8 TMEM columns of packed bf16 / 16 V rows
-          umma_ts(tmem_base + 256 + t * 64, tmem_base + t * 128 + k * 8, bdesc + k * (2048 >> 4), idesc_o,
-                  accumulate || k != 0);
-      };
+#define VF_ISSUE_S(T, KSTAGE)                                                                        \
+  do {                                                                                               \
+    if (elect_one()) {                                                                               \
+      const uint64_t a_ = q_desc + (T) * TILE_DESC;                                                  \
+      const uint64_t b_ = k_desc + (KSTAGE) * TILE_DESC;                                             \
+      _Pragma("unroll") for (int k_ = 0; k_ < 4; ++k_)                                               \
+          umma_ss(tmem_base + (T) * 128, a_ + 2 * k_, b_ + 2 * k_, idesc_s, k_ != 0);                \
+      umma_commit(&s_full[T]);                                                                       \
+    }                                                                                                \
+    __syncwarp();                                                                                    \
+  } while (0)
+#define VF_ISSUE_PV(T, VSTAGE, ACC)                                                                  \
+  do {                                                                                               \
+    if (elect_one()) {                                                                               \
+      const uint64_t b_ = v_desc + (VSTAGE) * TILE_DESC;                                             \
+      _Pragma("unroll") for (int k_ = 0; k_ < 8; ++k_) /* 16 keys: 8 TMEM cols of bf16x2, 16 V rows */ \
+          umma_ts(tmem_base + 256 + (T) * 64, tmem_base + (T) * 128 + k_ * 8, b_ + k_ * (2048 >> 4),  \
+                  idesc_o, (ACC) || k_ != 0);                                                        \
+    }                                                                                                \
+    __syncwarp();                                                                                    \
+  } while (0)
+#define VF_COMMIT(BAR)                                                                               \
+  do {                                                                                               \
+    if (elect_one()) umma_commit(BAR);                                                               \
+    __syncwarp();                                                                                    \
+  } while (0)
 
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
         const int qb = item % p.n_qblk;
         const bool t1 = qb * 256 + 128 < p.S;  // second query tile has at least one valid row
         att_wait(q_full, qph);
         // O_t / S_t of the previous item must have been drained by the softmax warpgroups
-        att_wait(&o_empty[0], oeph[0] ^ 1); oeph[0] ^= 1;
-        if (t1) { att_wait(&o_empty[1], oeph[1] ^ 1); oeph[1] ^= 1; }
-        tc_fence_after();
+        att_wait(&o_empty[0], oeph0 ^ 1); oeph0 ^= 1;
+        if (t1) { att_wait(&o_empty[1], oeph1 ^ 1); oeph1 ^= 1; }
 
         // prologue: S_t(0)
         att_wait(&k_full[ks], kph);
         tc_fence_after();
-        issue_s(0, ks);
-        if (t1) issue_s(1, ks);
-        umma_commit(&k_empty[ks]);
-        if (p.n_kt == 1) umma_commit(q_empty);
+        VF_ISSUE_S(0, ks);
+        if (t1) VF_ISSUE_S(1, ks);
+        VF_COMMIT(&k_empty[ks]);
+        if (p.n_kt == 1) VF_COMMIT(q_empty);
         if (++ks == KV_STAGES) { ks = 0; kph ^= 1; }
 
         for (int j = 0; j < p.n_kt; ++j) {
           const bool more = (j + 1 < p.n_kt);
           att_wait(&v_full[vs], vph);
-          att_wait(&p_full[0], pph[0]); pph[0] ^= 1;
+          att_wait(&p_full[0], pph0); pph0 ^= 1;
           tc_fence_after();
-          issue_pv(0, vs, j > 0);
+          VF_ISSUE_PV(0, vs, j > 0);
           if (more) {
             att_wait(&k_full[ks], kph);
             tc_fence_after();
-            issue_s(0, ks);
+            VF_ISSUE_S(0, ks);
           }
           if (t1) {
-            att_wait(&p_full[1], pph[1]); pph[1] ^= 1;
+            att_wait(&p_full[1], pph1); pph1 ^= 1;
             tc_fence_after();
-            issue_pv(1, vs, j > 0);
-            if (more) issue_s(1, ks);
+            VF_ISSUE_PV(1, vs, j > 0);
+            if (more) VF_ISSUE_S(1, ks);
           }
-          umma_commit(&v_empty[vs]);
+          VF_COMMIT(&v_empty[vs]);
           if (++vs == KV_STAGES) { vs = 0; vph ^= 1; }
           if (more) {
-            umma_commit(&k_empty[ks]);
-            if (j + 2 == p.n_kt) umma_commit(q_empty);  // last S MMAs of this item are in flight
+            VF_COMMIT(&k_empty[ks]);
+            if (j + 2 == p.n_kt) VF_COMMIT(q_empty);  // last S MMAs of this item are in flight
             if (++ks == KV_STAGES) { ks = 0; kph ^= 1; }
           }
         }
-        umma_commit(&o_full[0]);
-        if (t1) umma_commit(&o_full[1]);
+        VF_COMMIT(&o_full[0]);
+        if (t1) VF_COMMIT(&o_full[1]);
         qph ^= 1;
       }
-    }
+#undef VF_ISSUE_S
+#undef VF_ISSUE_PV
+#undef VF_COMMIT
     }
   } else {
     // ------------------------------------------------------------------ softmax warpgroups

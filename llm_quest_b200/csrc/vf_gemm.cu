@@ -90,7 +90,7 @@ __device__ __forceinline__ float gelu_erf_f(float x) {
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
 }
 
-template <int EPI, int BN>
+template <int EPI, int BN, bool PATCH>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
             const __grid_constant__ CUtensorMap tmB) {
@@ -135,7 +135,7 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
         const int n_blk = tile % p.num_n_blk;
         const int m_blk = tile / p.num_n_blk;
         int pc2 = 0, pc3 = 0, pimg = 0;  // patch mode: pw0, ph0, (b*C)*T + t'*tp
-        if (p.patch) {
+        if (PATCH) {
           int t = m_blk;
           const int pwb = t % p.n_pwb; t /= p.n_pwb;
           const int phb = t % p.n_phb; t /= p.n_phb;
@@ -150,7 +150,7 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
           uint8_t* a_dst = smem + stage * L::STAGE_BYTES;
           uint8_t* b_dst = a_dst + L::A_BYTES;
           mbar_expect_tx(&full_bar[stage], L::STAGE_BYTES);
-          if (p.patch) {
+          if (PATCH) {
             // K index = ((c*tp + dt)*P + py)*P + px ; one 64-wide k-block = (64/P) pixel rows.
             const int rows_per_kb = BK / p.P;
             const int kb_per_plane = p.P / rows_per_kb;       // k-blocks per (c,dt) plane
@@ -184,7 +184,7 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
           const uint32_t a_addr = smem_u32(smem + stage * L::STAGE_BYTES);
           const uint64_t a_desc = umma_desc_sw128(a_addr);
           const uint64_t b_desc = umma_desc_sw128(a_addr + L::A_BYTES);
-          if (p.patch) {
+          if (PATCH) {
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k)  // slice k = pixel row py0+k: [16 ph][8 pw][32 B], SBO 1024 B
               umma_ss(d_tmem, umma_desc_sw32(a_addr + k * 256, 1024), b_desc + 2 * k, idesc, (kb | k) != 0);
@@ -209,23 +209,31 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
     // (conflict-free) shared-memory buffer and does all epilogue math + I/O in the coalesced mapping:
     // lane l owns columns 4*(l%8)..+3 of rows (l/8)+4i, i = 0..7.
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
-    float* stA = reinterpret_cast<float*>(smem + L::EPI_OFF + (warp - 2) * 8192);
-    float* stB = stA + 1024;
+    // staging blocks are addressed in the shared window explicitly (ld/st.shared), never through
+    // generic pointers
+    const uint32_t stA = smem_u32(smem + L::EPI_OFF + (warp - 2) * 8192);
+    const uint32_t stB = stA + 4096;
     const int cl = lane & 7;       // 16-byte column group inside a 32-column block
     const int rl = lane >> 3;      // row offset inside a group of 4 rows
     int acc = 0;
     uint32_t acc_phase = 0;
 
     // write this thread's accumulator row (32 fp32) into the staging block, chunk j -> slot j ^ (row & 7)
-    auto stage_row = [&](float* st, const uint32_t* r) {
-      float4* row = reinterpret_cast<float4*>(st + lane * 32);
+    auto stage_row = [&](uint32_t st, const uint32_t* r) {
+      const uint32_t row = st + lane * 128;
 #pragma unroll
       for (int j = 0; j < 8; ++j)
-        row[j ^ (lane & 7)] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
-                                          __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row + ((j ^ (lane & 7)) << 4)), "r"(r[4 * j]),
+                     "r"(r[4 * j + 1]), "r"(r[4 * j + 2]), "r"(r[4 * j + 3])
+                     : "memory");
     };
-    auto read_staged = [&](const float* st, int rr) {
-      return reinterpret_cast<const float4*>(st + rr * 32)[cl ^ (rr & 7)];
+    auto read_staged = [&](uint32_t st, int rr) {
+      float4 v;
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                   : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                   : "r"(st + rr * 128 + ((cl ^ (rr & 7)) << 4))
+                   : "memory");
+      return v;
     };
 
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -233,37 +241,48 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
       const int m_blk = tile / p.num_n_blk;
       const int col0 = n_blk * BN;
 
-      // ---- output row (element offset / validity) of the 8 rows this lane touches
+      // ---- output row (or -1) of the 8 rows this lane touches: rows r0, r0+4, ..., r0+28 of the tile.
+      // One integer division per tile at most; the other rows follow incrementally.
       long long orow[8];
-      int aux[8];  // patch: spatial index (pos row); rope: table row; otherwise unused
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int r_local = quarter * 32 + rl + 4 * i;
-        long long o = -1;
-        int ax = 0;
-        if (p.patch) {
+      int aux[8];  // patch: spatial index (pos-embed row); rope: cos/sin table row
+      {
+        const int r0 = quarter * 32 + rl;
+        if constexpr (PATCH) {
           int t = m_blk;
           const int pwb = t % p.n_pwb; t /= p.n_pwb;
           const int phb = t % p.n_phb; t /= p.n_phb;
           const int tpr = t % p.Tp;
           const int b = t / p.Tp;
-          const int ph = phb * p.PH + r_local / p.PW;
-          const int pw = pwb * p.PW + r_local % p.PW;
-          if (ph < p.nh && pw < p.nw) {
-            ax = ph * p.nw + pw;
-            o = (long long)b * p.grp_stride + p.row_off + (long long)tpr * p.nh * p.nw + ax;
+          const long long base = (long long)b * p.grp_stride + p.row_off + (long long)tpr * p.nh * p.nw;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r_local = r0 + 4 * i;          // tile rows are a 16 x 8 rectangle of patches
+            const int ph = phb * 16 + (r_local >> 3);
+            const int pw = pwb * 8 + (r_local & 7);
+            const bool ok = ph < p.nh && pw < p.nw;
+            aux[i] = ok ? ph * p.nw + pw : 0;
+            orow[i] = ok ? base + aux[i] : -1;
           }
         } else {
-          const int m = m_blk * BM + r_local;
-          if (m < p.M) {
-            if (EPI == VF_EPI_SCATTER_BF16) o = p.dst_rows[m];
-            else if (p.grp_rows > 0) o = (long long)(m / p.grp_rows) * p.grp_stride + (m % p.grp_rows) + p.row_off;
-            else o = m;
-            if (EPI == VF_EPI_QKV_ROPE_BF16) ax = m % p.rope_period;
+          const int m0 = m_blk * BM + r0;
+          int q = 0, rem = 0;                         // remap / rope: running quotient and remainder
+          if (EPI == VF_EPI_QKV_ROPE_BF16) rem = m0 % p.rope_period;
+          else if (p.grp_rows > 0) { q = m0 / p.grp_rows; rem = m0 - q * p.grp_rows; }
+          const int period = EPI == VF_EPI_QKV_ROPE_BF16 ? p.rope_period : p.grp_rows;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int m = m0 + 4 * i;
+            long long o = m;
+            if (EPI == VF_EPI_SCATTER_BF16) o = m < p.M ? p.dst_rows[m] : -1;
+            else if (EPI != VF_EPI_QKV_ROPE_BF16 && p.grp_rows > 0) o = (long long)q * p.grp_stride + rem + p.row_off;
+            orow[i] = m < p.M ? o : -1;
+            aux[i] = rem;
+            if (period > 0) {
+              rem += 4;
+              while (rem >= period) { rem -= period; ++q; }
+            }
           }
         }
-        orow[i] = o;
-        aux[i] = ax;
       }
 
       wait_or_trap(&tfull_bar[acc], acc_phase);
@@ -370,7 +389,7 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
               }
             }
           }
-          if (p.patch && p.pos) {
+          if (PATCH && p.pos) {
 #pragma unroll
             for (int i = 0; i < 8; ++i)
               ex[i] = __ldg(reinterpret_cast<const float4*>(p.pos + (long long)aux[i] * p.ld_pos + cc));
@@ -426,12 +445,12 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-template <int EPI, int BN>
+template <int EPI, int BN, bool PATCH = false>
 static int launch_gemm(const GemmParams& p, const CUtensorMap& tmA, const CUtensorMap& tmB,
                        cudaStream_t stream) {
   using L = SmemLayout<BN>;
   static bool configured = false;
-  auto kfn = gemm_kernel<EPI, BN>;
+  auto kfn = gemm_kernel<EPI, BN, PATCH>;
   if (!configured) {
     VF_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     configured = true;
@@ -601,6 +620,6 @@ extern "C" int vf_patch_embed(const void* pixels, int32_t B, int32_t C, int32_t 
     if (e) return e;
   }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  return bn == 256 ? launch_gemm<VF_EPI_BIAS_F32, 256>(p, tmA, tmB, s)
-                   : launch_gemm<VF_EPI_BIAS_F32, 128>(p, tmA, tmB, s);
+  return bn == 256 ? launch_gemm<VF_EPI_BIAS_F32, 256, true>(p, tmA, tmB, s)
+                   : launch_gemm<VF_EPI_BIAS_F32, 128, true>(p, tmA, tmB, s);
 }

@@ -1,5 +1,5 @@
 #!/bin/bash
-# ncu evidence: (1) launch list with device time per launch, (2) full capture of the dominant kernels
+# ncu evidence: full capture of the dominant kernels (one forward pass of cfg-2 after one warm-up pass)
 mkdir -p gpurun_out
 cat > /tmp/one_step.py <<'PY'
 import sys, torch
@@ -15,10 +15,10 @@ with torch.inference_mode():
         m(x)
 torch.cuda.synchronize()
 PY
+if [ "$1" = "list" ]; then
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv python /tmp/one_step.py 2 > gpurun_out/ncu_list.log 2>&1
 echo "list exit=$?"
-ncu --set full --clock-control none --import-source on -k regex:gemm_kernel -s 54 -c 8 -o gpurun_out/prof_gemm -f python /tmp/one_step.py 2 > gpurun_out/ncu_gemm.log 2>&1
+fi
+ncu --set full --clock-control none --import-source on -k regex:gemm_kernel -s 54 -c 4 -o gpurun_out/prof_gemm -f python /tmp/one_step.py 2 > gpurun_out/ncu_gemm.log 2>&1
 echo "gemm exit=$?"
-ncu --set full --clock-control none --import-source on -k regex:attention_kernel -s 12 -c 1 -o gpurun_out/prof_attn -f python /tmp/one_step.py 2 > gpurun_out/ncu_attn.log 2>&1
-echo "attn exit=$?"
 ls -la gpurun_out/*.ncu-rep
