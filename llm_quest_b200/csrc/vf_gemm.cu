@@ -29,7 +29,14 @@ namespace vf {
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int STAGES = 4;
-constexpr int GEMM_THREADS = 192;  // warp0 TMA, warp1 MMA, warps 2-5 epilogue
+// warp0 TMA, warp1 MMA, then the epilogue warps: 4 for the QKV+RoPE epilogue (it needs two staging
+// blocks per warp), 8 for every other epilogue (two warps per TMEM lane quarter, each taking half of
+// the tile's columns — the epilogue is latency-bound, so the extra warps are what hides it).
+template <int EPI>
+struct EpiCfg {
+  static constexpr int WARPS = (EPI == VF_EPI_QKV_ROPE_BF16) ? 4 : 8;
+  static constexpr int THREADS = 64 + 32 * WARPS;
+};
 
 struct GemmParams {
   int M, N, K;
@@ -64,7 +71,7 @@ struct SmemLayout {
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
-  static constexpr int EPI_OFF = BAR_OFF + 256;            // 4 epilogue warps x 2 staging blocks of 32x32 fp32
+  static constexpr int EPI_OFF = BAR_OFF + 256;            // 32 KB of 32x32 fp32 staging blocks for the epilogue warps
   static constexpr int TOTAL = EPI_OFF + 4 * 8192 + 1024;  // + alignment slack
 };
 
@@ -91,7 +98,7 @@ __device__ __forceinline__ float gelu_erf_f(float x) {
 }
 
 template <int EPI, int BN, bool PATCH>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(EpiCfg<EPI>::THREADS, 1)
 gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
             const __grid_constant__ CUtensorMap tmB) {
   using L = SmemLayout<BN>;
@@ -116,7 +123,7 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], 4);  // one arrival per epilogue warp
+      mbar_init(&tempty_bar[a], EpiCfg<EPI>::WARPS);  // one arrival per epilogue warp
     }
     fence_barrier_init();
   }
@@ -211,8 +218,11 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
     // staging blocks are addressed in the shared window explicitly (ld/st.shared), never through
     // generic pointers
-    const uint32_t stA = smem_u32(smem + L::EPI_OFF + (warp - 2) * 8192);
-    const uint32_t stB = stA + 4096;
+    constexpr int EW = EpiCfg<EPI>::WARPS;
+    constexpr int COLS_PER_WARP = BN / (EW / 4);      // columns of the tile this warp drains
+    const int chalf = (warp - 2) >> 2;                // 0, or 0/1 with eight warps
+    const uint32_t stA = smem_u32(smem + L::EPI_OFF + (warp - 2) * (32768 / EW));
+    const uint32_t stB = stA + 4096;                  // second block: RoPE epilogue only
     const int cl = lane & 7;       // 16-byte column group inside a 32-column block
     const int rl = lane >> 3;      // row offset inside a group of 4 rows
     int acc = 0;
@@ -287,7 +297,7 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
 
       wait_or_trap(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + chalf * COLS_PER_WARP;
 
       if constexpr (EPI == VF_EPI_QKV_ROPE_BF16) {
         __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(p.out);
@@ -349,13 +359,13 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
         uint32_t r[32];
         tmem_ld_x32(t_row, r);
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = 0; c < COLS_PER_WARP / 32; ++c) {
           tmem_ld_wait();
           __syncwarp();                          // previous block fully consumed by all lanes
           stage_row(stA, r);
-          if (c + 1 < BN / 32) tmem_ld_x32(t_row + (c + 1) * 32, r);  // overlaps the math below
+          if (c + 1 < COLS_PER_WARP / 32) tmem_ld_x32(t_row + (c + 1) * 32, r);  // overlaps the math below
           __syncwarp();
-          const int cbase = col0 + c * 32;
+          const int cbase = col0 + chalf * COLS_PER_WARP + c * 32;
           const int cc = cbase + cl * 4;         // first of this lane's 4 columns
           if (cc >= p.N) continue;
           const bool vec = p.vec_ok && (cc + 4 <= p.N);
@@ -459,7 +469,7 @@ static int launch_gemm(const GemmParams& p, const CUtensorMap& tmA, const CUtens
   VF_REQUIRE(sms > 0, VF_ERR_NO_DEVICE, "no CUDA device");
   const int tiles = p.num_m_blk * p.num_n_blk;
   const int grid = tiles < sms ? tiles : sms;
-  kfn<<<grid, GEMM_THREADS, L::TOTAL, stream>>>(p, tmA, tmB);
+  kfn<<<grid, EpiCfg<EPI>::THREADS, L::TOTAL, stream>>>(p, tmA, tmB);
   count_launch();
   VF_CUDA(cudaGetLastError());
   return VF_OK;
