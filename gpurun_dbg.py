@@ -1,22 +1,18 @@
-import sys, torch
+import sys, torch, os, subprocess
 sys.path.insert(0, '.')
-from llm_quest_b200 import _lib as L
-from oracle import vision_oracle as VO
-variant = sys.argv[1]
-B,T,H,W,D = 2,2,64,96,128
-P,tp=16,2
-g = torch.Generator().manual_seed(0)
-x = torch.randn(B,3,T,H,W,generator=g).to(torch.bfloat16)
-w = (torch.randn(D,3,tp,P,P,generator=g)*0.03).to(torch.bfloat16)
-b = torch.randn(D,generator=g)
-n=(H//P)*(W//P); S=(T//tp)*n
-pos = torch.randn(n+5,D,generator=g)
-out = torch.full((B*S,D), float('nan'), device='cuda')
-xd, wd, bd, pd = x.cuda(), w.reshape(D,-1).contiguous().cuda(), b.cuda(), pos.cuda()
-if variant == 'nopos': pd = None
-if variant == 'nobias': bd = None; pd = None
-L.patch_embed(xd, wd, bd, pd, out, P, tp, S, 0)
-torch.cuda.synchronize()
-ref = VO.patch_embed3d(x.float(), w.float(), b if bd is not None else torch.zeros(D))
-if pd is not None: ref = ref + pos[:n].repeat(T//tp,1)[None]
-print(variant, 'err', VO.max_norm_err(out.cpu().view(B,S,D), ref))
+if len(sys.argv) > 1:
+    from llm_quest_b200 import _lib as L
+    B,S,H = 64,784,12
+    qkv = torch.randn(B*S, 3*H*64, device='cuda').to(torch.bfloat16)
+    out = torch.empty(B*S, H*64, device='cuda', dtype=torch.bfloat16)
+    for _ in range(3): L.attention(qkv, out, B, S, H, 0.125)
+    torch.cuda.synchronize()
+    e0=torch.cuda.Event(enable_timing=True); e1=torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10): L.attention(qkv, out, B, S, H, 0.125)
+    e1.record(); torch.cuda.synchronize()
+    ms=e0.elapsed_time(e1)/10
+    print('skew', os.environ.get('VF_ATTN_SKEW'), 'ms', round(ms,4), 'TF', round(4*B*H*S*S*64/ms/1e9,1))
+else:
+    for sk in [0, 250, 500, 800, 1200]:
+        subprocess.run([sys.executable, __file__, 'x'], env={**os.environ, 'VF_ATTN_SKEW': str(sk)})

@@ -12,11 +12,16 @@
 //
 //   one persistent CTA per SM; a work item is (sample b, head h, block of 512 queries) = FOUR
 //   128-row query tiles that share every 64-key K/V tile:
-//     warp 0        TMA loader: Q0..Q3 once per item; K and V tiles through two 4-stage rings
-//     warp 1        tcgen05.mma issuer:  S_t = Q_t K_j^T  (SS, M=128, N=64,  K=64)
-//                                        O_t += P_t V_j   (TS: P_t bf16 in TMEM; V MN-major smem)
-//     warps 4..19   four softmax warpgroups (one per query tile), one thread per query row:
+//     warps 0..15   four softmax warpgroups (one per query tile), one thread per query row:
 //                   rowmax / exp2 / rowsum / P->TMEM / lazy O rescale / final O/l store
+//     warp 16       TMA loader: Q0..Q3 once per item; K and V tiles through two 4-stage rings
+//     warps 17,18   tcgen05.mma issuers (tiles {0,1} and {2,3}):
+//                                        S_t = Q_t K_j^T  (SS, M=128, N=64,  K=64)
+//                                        O_t += P_t V_j   (TS: P_t bf16 in TMEM; V MN-major smem)
+//                   Measured: one issuer needs ~380 cycles to issue the 8 small MMAs of a tile-step,
+//                   more than the 256 tensor cycles they take, so a single issuer starves all four
+//                   softmax chains; two issuers halve that. They carry the HIGHEST warp ids of their
+//                   sub-partitions because the warp scheduler favours high warp ids.
 //   TMEM (512 cols): S_t at [64t, 64t+64), P_t aliases the first 32 columns of S_t (64 bf16),
 //                    O_t at [256+64t, 256+64t+64).
 //   Each softmax warp sits on one SM sub-partition together with the three warps that own the same
@@ -26,6 +31,7 @@
 #include "vf_common.cuh"
 
 #include <math.h>
+#include <stdlib.h>
 
 namespace vf {
 
@@ -33,6 +39,8 @@ constexpr int NQ = 4;                       // query tiles per work item
 constexpr int KT = 64;                      // keys per K/V tile
 constexpr int ATT_THREADS = 128 + NQ * 128;
 constexpr int KV_STAGES = 4;
+constexpr int LOADER_WARP = NQ * 4;      // warp 16 (sub-partition 0)
+constexpr int MMA_WARP = NQ * 4 + 1;     // warps 17, 18 (sub-partitions 1, 2): two tiles each
 constexpr int Q_TILE_BYTES = 128 * 64 * 2;  // 16 KB
 constexpr int KV_TILE_BYTES = KT * 64 * 2;  // 8 KB
 
@@ -43,12 +51,13 @@ struct AttnParams {
   int n_items;     // B * H * n_qblk
   int n_bh;        // B * H
   float scale_log2;
+  int skew;        // cycles between the start of consecutive softmax chains (0 = none)
   __nv_bfloat16* out;
 };
 
 struct AttnSmem {
-  static constexpr int Q_OFF = 0;
-  static constexpr int K_OFF = NQ * Q_TILE_BYTES;
+  static constexpr int Q_OFF = 0;                               // 2 buffers x NQ tiles (next item's Q loads early)
+  static constexpr int K_OFF = 2 * NQ * Q_TILE_BYTES;
   static constexpr int V_OFF = K_OFF + KV_STAGES * KV_TILE_BYTES;
   static constexpr int BAR_OFF = V_OFF + KV_STAGES * KV_TILE_BYTES;
   static constexpr int TOTAL = BAR_OFF + 512 + 1024;
@@ -85,9 +94,9 @@ attention_kernel(const AttnParams p, const __grid_constant__ CUtensorMap tmQ,
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AttnSmem::BAR_OFF);
-  uint64_t* q_full = bars + 0;
-  uint64_t* q_empty = bars + 1;
-  uint64_t* k_full = bars + 2;                  // [KV_STAGES]
+  uint64_t* q_full = bars + 0;                  // [2]
+  uint64_t* q_empty = bars + 2;                 // [2]
+  uint64_t* k_full = bars + 4;                  // [KV_STAGES]
   uint64_t* k_empty = k_full + KV_STAGES;
   uint64_t* v_full = k_empty + KV_STAGES;
   uint64_t* v_empty = v_full + KV_STAGES;
@@ -100,16 +109,18 @@ attention_kernel(const AttnParams p, const __grid_constant__ CUtensorMap tmQ,
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == LOADER_WARP && lane == 0) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmKV);
-    mbar_init(q_full, 1);
-    mbar_init(q_empty, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&q_full[i], 1);
+      mbar_init(&q_empty[i], 2);   // both MMA issuers
+    }
     for (int s = 0; s < KV_STAGES; ++s) {
       mbar_init(&k_full[s], 1);
-      mbar_init(&k_empty[s], 1);
+      mbar_init(&k_empty[s], 2);
       mbar_init(&v_full[s], 1);
-      mbar_init(&v_empty[s], 1);
+      mbar_init(&v_empty[s], 2);
     }
     for (int t = 0; t < NQ; ++t) {
       mbar_init(&s_full[t], 1);
@@ -119,33 +130,35 @@ attention_kernel(const AttnParams p, const __grid_constant__ CUtensorMap tmQ,
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  if (warp == MMA_WARP) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < 4) {
+  if (warp >= NQ * 4) {
     // loader / MMA / idle warps: hand registers to the softmax warpgroups. Budget: the CTA owns
     // 640 x 96 registers at launch; 128 x 56 + 512 x 104 fits inside that pool (setmaxnreg.inc can
     // only draw from what the CTA already holds — asking for more deadlocks the warpgroup).
     asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
-    if (warp == 0) {
+    if (warp == LOADER_WARP) {
       // ---------------------------------------------------------------- TMA loader
       if (lane == 0) {
         int ks = 0, vs = 0;
-        uint32_t kph = 0, vph = 0, qph = 0;
+        uint32_t kph = 0, vph = 0, qph = 0;   // qph: bit i = phase of q buffer i
+        int qbuf = 0;
         for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
           int b, h, qb;
           decode_item(p, item, b, h, qb);
           const int row0 = b * p.S;
-          att_wait(q_empty, qph ^ 1);
-          mbar_expect_tx(q_full, NQ * Q_TILE_BYTES);
+          att_wait(&q_empty[qbuf], ((qph >> qbuf) & 1) ^ 1);
+          mbar_expect_tx(&q_full[qbuf], NQ * Q_TILE_BYTES);
 #pragma unroll
           for (int t = 0; t < NQ; ++t)
-            tma_load_2d(smem + AttnSmem::Q_OFF + t * Q_TILE_BYTES, &tmQ, q_full, h * 64,
+            tma_load_2d(smem + AttnSmem::Q_OFF + (qbuf * NQ + t) * Q_TILE_BYTES, &tmQ, &q_full[qbuf], h * 64,
                         row0 + qb * (128 * NQ) + t * 128);
-          qph ^= 1;
+          qph ^= 1u << qbuf;
+          qbuf ^= 1;
           for (int j = 0; j < p.n_kt; ++j) {
             att_wait(&k_empty[ks], kph ^ 1);
             mbar_expect_tx(&k_full[ks], KV_TILE_BYTES);
@@ -160,8 +173,9 @@ attention_kernel(const AttnParams p, const __grid_constant__ CUtensorMap tmQ,
           }
         }
       }
-    } else if (warp == 1) {
-      // ---------------------------------------------------------------- MMA issuer
+    } else if (warp == MMA_WARP || warp == MMA_WARP + 1) {
+      // ---------------------------------------------------------------- MMA issuers
+      const int t_lo = (warp - MMA_WARP) * 2;   // this issuer owns query tiles t_lo, t_lo+1
       // The whole warp walks the (warp-uniform) schedule so that addresses and descriptors live in
       // uniform registers; one elected lane issues the tcgen05 instructions.
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, KT, 0, 0);   // Q K^T : both K-major
@@ -172,12 +186,13 @@ attention_kernel(const AttnParams p, const __grid_constant__ CUtensorMap tmQ,
       constexpr uint64_t QT_DESC = Q_TILE_BYTES >> 4;
       constexpr uint64_t KVT_DESC = KV_TILE_BYTES >> 4;
       int ks = 0, vs = 0;
-      uint32_t kph = 0, vph = 0, qph = 0;
+      uint32_t kph = 0, vph = 0, qph = 0;   // qph: bit i = phase of q buffer i
+      int qbuf = 0;
       uint32_t pph = 0, oeph = 0;   // bit t = phase of p_full[t] / o_empty[t]
 
       auto issue_s = [&](int t, int kstage) {
         if (elect_one()) {
-          const uint64_t a_ = q_desc + t * QT_DESC;
+          const uint64_t a_ = q_desc + (qbuf * NQ + t) * QT_DESC;
           const uint64_t b_ = k_desc + kstage * KVT_DESC;
 #pragma unroll
           for (int k_ = 0; k_ < 4; ++k_)      // head_dim 64 = 4 x K16
@@ -196,6 +211,24 @@ attention_kernel(const AttnParams p, const __grid_constant__ CUtensorMap tmQ,
         }
         __syncwarp();
       };
+      auto issue_pv_s = [&](int t, int vstage, bool accumulate, bool with_s, int kstage) {
+        if (elect_one()) {
+          const uint64_t bv_ = v_desc + vstage * KVT_DESC;
+#pragma unroll
+          for (int k_ = 0; k_ < KT / 16; ++k_)
+            umma_ts(tmem_base + 256 + t * 64, tmem_base + t * 64 + k_ * 8, bv_ + k_ * (2048 >> 4), idesc_o,
+                    accumulate || k_ != 0);
+          if (with_s) {
+            const uint64_t a_ = q_desc + (qbuf * NQ + t) * QT_DESC;
+            const uint64_t bk_ = k_desc + kstage * KVT_DESC;
+#pragma unroll
+            for (int k_ = 0; k_ < 4; ++k_)
+              umma_ss(tmem_base + t * 64, a_ + 2 * k_, bk_ + 2 * k_, idesc_s, k_ != 0);
+            umma_commit(&s_full[t]);
+          }
+        }
+        __syncwarp();
+      };
       auto commit = [&](uint64_t* bar) {
         if (elect_one()) umma_commit(bar);
         __syncwarp();
@@ -206,47 +239,57 @@ attention_kernel(const AttnParams p, const __grid_constant__ CUtensorMap tmQ,
         decode_item(p, item, b, h, qb);
         int nt = (p.S - qb * (128 * NQ) + 127) / 128;  // query tiles of this item with >= 1 valid row
         nt = nt > NQ ? NQ : nt;
-        att_wait(q_full, qph);
-        // O_t / S_t of the previous use of tile slot t must have been drained by its warpgroup
-        for (int t = 0; t < nt; ++t) {
-          att_wait(&o_empty[t], ((oeph >> t) & 1) ^ 1);
-          oeph ^= 1u << t;
-        }
-        // prologue: S_t(0)
+        att_wait(&q_full[qbuf], (qph >> qbuf) & 1);
+        const int t_hi = nt < t_lo + 2 ? nt : t_lo + 2;   // tiles [t_lo, t_hi) are mine (maybe none)
+        // prologue: S_t(0). S_t is free as soon as the previous item's last PV_t has retired (in-order
+        // pipe); only the first PV_t of this item has to wait for the warpgroup to drain O_t.
         att_wait(&k_full[ks], kph);
         tc_fence_after();
-        for (int t = 0; t < nt; ++t) issue_s(t, ks);
+        for (int t = t_lo; t < t_hi; ++t) {
+          if (item == static_cast<int>(blockIdx.x) && p.skew > 0) {
+            // One-time stagger of the four softmax chains (tile t starts t*skew cycles late): chains
+            // that run in lock-step fight for the MUFU and then all wait for their MMAs together.
+            const long long until = clock64() + static_cast<long long>(p.skew) * (t == t_lo ? t_lo : 1);
+            while (clock64() < until) {
+            }
+          }
+          issue_s(t, ks);
+        }
         commit(&k_empty[ks]);
-        if (p.n_kt == 1) commit(q_empty);
+        if (p.n_kt == 1) commit(&q_empty[qbuf]);
         if (++ks == KV_STAGES) { ks = 0; kph ^= 1; }
 
         for (int j = 0; j < p.n_kt; ++j) {
           const bool more = (j + 1 < p.n_kt);
           att_wait(&v_full[vs], vph);
           if (more) att_wait(&k_full[ks], kph);
-          for (int t = 0; t < nt; ++t) {
+          for (int t = t_lo; t < t_hi; ++t) {
             att_wait(&p_full[t], (pph >> t) & 1);
             pph ^= 1u << t;
+            if (j == 0) {  // O_t of the previous item drained?
+              att_wait(&o_empty[t], ((oeph >> t) & 1) ^ 1);
+              oeph ^= 1u << t;
+            }
             tc_fence_after();
-            issue_pv(t, vs, j > 0);
-            if (more) issue_s(t, ks);
+            issue_pv_s(t, vs, j > 0, more, ks);
           }
           commit(&v_empty[vs]);
           if (++vs == KV_STAGES) { vs = 0; vph ^= 1; }
           if (more) {
             commit(&k_empty[ks]);
-            if (j + 2 == p.n_kt) commit(q_empty);  // the last S MMAs of this item are in flight
+            if (j + 2 == p.n_kt) commit(&q_empty[qbuf]);  // the last S MMAs of this item are in flight
             if (++ks == KV_STAGES) { ks = 0; kph ^= 1; }
           }
         }
-        for (int t = 0; t < nt; ++t) commit(&o_full[t]);
-        qph ^= 1;
+        for (int t = t_lo; t < t_hi; ++t) commit(&o_full[t]);
+        qph ^= 1u << qbuf;
+        qbuf ^= 1;
       }
     }
   } else {
     // ------------------------------------------------------------------ softmax warpgroups
     asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
-    const int t = (warp - 4) >> 2;        // query tile 0..3
+    const int t = warp >> 2;              // query tile 0..3
     const int quarter = warp & 3;         // TMEM lane quarter (== SM sub-partition)
     const uint32_t lane_sel = static_cast<uint32_t>(quarter * 32) << 16;
     const uint32_t s_addr = tmem_base + lane_sel + t * 64;
@@ -357,7 +400,7 @@ attention_kernel(const AttnParams p, const __grid_constant__ CUtensorMap tmQ,
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == MMA_WARP) {
     tc_fence_after();
     tmem_dealloc<512>(tmem_base);
   }
@@ -383,6 +426,10 @@ extern "C" int vf_attention_fwd(const void* qkv, void* out, int32_t B, int32_t S
   p.n_items = p.n_bh * p.n_qblk;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
+  {
+    const char* e = getenv("VF_ATTN_SKEW");
+    p.skew = e ? atoi(e) : 500;
+  }
 
   CUtensorMap tmQ, tmKV;
   uint64_t dims[2] = {(uint64_t)3 * H * 64, (uint64_t)B * S};

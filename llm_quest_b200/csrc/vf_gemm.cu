@@ -23,6 +23,7 @@
 #include "../../include/vfuse.h"
 
 #include <math.h>
+#include <type_traits>
 
 namespace vf {
 
@@ -87,11 +88,13 @@ __device__ __forceinline__ void wait_or_trap(uint64_t* bar, uint32_t parity) {
 }
 
 __device__ __forceinline__ float gelu_tanh_f(float x) {
-  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
-  float u = k0 * x * fmaf(k1, x * x, 1.0f);
+  // 0.5 x (1 + tanh(k0 (x + k1 x^3))) with the constants folded: 3 FMA-pipe ops, 1 MUFU, 2 more
+  const float k0 = 0.7978845608028654f, k01 = 0.7978845608028654f * 0.044715f;
+  const float u = x * fmaf(x * x, k01, k0);
   float t;
   asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
-  return 0.5f * x * (1.0f + t);
+  const float h = 0.5f * x;
+  return fmaf(h, t, h);
 }
 __device__ __forceinline__ float gelu_erf_f(float x) {
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
@@ -356,6 +359,20 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
         }
       } else {
         constexpr bool OUT_F32 = (EPI == VF_EPI_BIAS_F32 || EPI == VF_EPI_BIAS_RES_F32);
+        constexpr int ESZ = OUT_F32 ? 4 : 2;
+        // Uniform fast path: 16-byte aligned rows and N % 4 == 0, so a lane's 4 columns are either all
+        // inside the matrix or all outside and every access is one vector instruction.
+        const bool fast = p.vec_ok && ((p.N & 3) == 0);
+        const bool rows_all_valid = !PATCH && EPI != VF_EPI_SCATTER_BF16 && (m_blk + 1) * BM <= p.M;
+        // per-row base pointers, once per tile (rows that are masked out point at row 0 and never store)
+        char* obase[8];
+        const char* rbase[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const long long o = orow[i] < 0 ? 0 : orow[i];
+          obase[i] = reinterpret_cast<char*>(p.out) + o * p.ldo * ESZ;
+          rbase[i] = EPI == VF_EPI_BIAS_RES_F32 ? reinterpret_cast<const char*>(p.res) + o * p.ldr * 4 : nullptr;
+        }
         uint32_t r[32];
         tmem_ld_x32(t_row, r);
 #pragma unroll 1
@@ -365,72 +382,68 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
           stage_row(stA, r);
           if (c + 1 < COLS_PER_WARP / 32) tmem_ld_x32(t_row + (c + 1) * 32, r);  // overlaps the math below
           __syncwarp();
-          const int cbase = col0 + chalf * COLS_PER_WARP + c * 32;
-          const int cc = cbase + cl * 4;         // first of this lane's 4 columns
+          const int cc = col0 + chalf * COLS_PER_WARP + c * 32 + cl * 4;   // first of this lane's 4 columns
           if (cc >= p.N) continue;
-          const bool vec = p.vec_ok && (cc + 4 <= p.N);
-          float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (p.bias) {
-            if (cc + 4 <= p.N) bv = __ldg(reinterpret_cast<const float4*>(p.bias + cc));
-            else {
-              bv.x = p.bias[cc];
-              if (cc + 1 < p.N) bv.y = p.bias[cc + 1];
-              if (cc + 2 < p.N) bv.z = p.bias[cc + 2];
-            }
-          }
-          // residual / pos-embed rows are fetched for all 8 rows up front (they may alias `out`, so the
-          // compiler cannot hoist them across the stores itself); rows that are masked out read row 0
-          float4 ex[8];
+          if (fast) {
+            float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.bias) bv = __ldg(reinterpret_cast<const float4*>(p.bias + cc));
+            // residual / pos-embed values of all 8 rows are fetched up front: they may alias `out`, so
+            // the compiler cannot hoist them across the stores by itself
+            float4 ex[8];
+            if constexpr (EPI == VF_EPI_BIAS_RES_F32) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) ex[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if constexpr (EPI == VF_EPI_BIAS_RES_F32) {
-            if (vec) {
+              for (int i = 0; i < 8; ++i) ex[i] = *reinterpret_cast<const float4*>(rbase[i] + cc * 4);
+            }
+            if constexpr (PATCH) {
 #pragma unroll
               for (int i = 0; i < 8; ++i)
-                ex[i] = *reinterpret_cast<const float4*>(p.res + (orow[i] < 0 ? 0 : orow[i]) * p.ldr + cc);
-            } else {
+                ex[i] = p.pos ? __ldg(reinterpret_cast<const float4*>(p.pos + (long long)aux[i] * p.ld_pos + cc))
+                              : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            // rows_all_valid (uniform): no per-row branch at all, so the 8 rows interleave freely
+            auto do_rows = [&](auto guarded) {
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
-                const float* rp = p.res + (orow[i] < 0 ? 0 : orow[i]) * p.ldr + cc;
-                ex[i].x = rp[0];
-                if (cc + 1 < p.N) ex[i].y = rp[1];
-                if (cc + 2 < p.N) ex[i].z = rp[2];
-                if (cc + 3 < p.N) ex[i].w = rp[3];
+                const float4 x = read_staged(stA, rl + 4 * i);
+                float v[4] = {x.x + bv.x, x.y + bv.y, x.z + bv.z, x.w + bv.w};
+                if constexpr (EPI == VF_EPI_BIAS_RES_F32 || PATCH) {
+                  v[0] += ex[i].x; v[1] += ex[i].y; v[2] += ex[i].z; v[3] += ex[i].w;
+                }
+                if constexpr (EPI == VF_EPI_GELU_TANH_BF16) {
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) v[e] = gelu_tanh_f(v[e]);
+                }
+                if constexpr (EPI == VF_EPI_GELU_ERF_BF16) {
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) v[e] = gelu_erf_f(v[e]);
+                }
+                if (!decltype(guarded)::value || orow[i] >= 0) {
+                  if constexpr (OUT_F32)
+                    *reinterpret_cast<float4*>(obase[i] + cc * 4) = make_float4(v[0], v[1], v[2], v[3]);
+                  else
+                    *reinterpret_cast<uint2*>(obase[i] + cc * 2) = make_uint2(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]));
+                }
               }
-            }
-          }
-          if (PATCH && p.pos) {
+            };
+            if (rows_all_valid) do_rows(std::false_type{});
+            else do_rows(std::true_type{});
+          } else {
+            // generic path (unaligned rows or N % 4 != 0, e.g. a 10-class head): scalar, per-element guards
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
-              ex[i] = __ldg(reinterpret_cast<const float4*>(p.pos + (long long)aux[i] * p.ld_pos + cc));
-          }
+            for (int i = 0; i < 8; ++i) {   // unrolled so that the per-row arrays stay in registers
+              if (orow[i] < 0) continue;
+              const float4 x = read_staged(stA, rl + 4 * i);
+              const float xv[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float4 x = read_staged(stA, rl + 4 * i);
-            float v[4] = {x.x + bv.x + ex[i].x, x.y + bv.y + ex[i].y, x.z + bv.z + ex[i].z, x.w + bv.w + ex[i].w};
-            if constexpr (EPI == VF_EPI_GELU_TANH_BF16) {
-#pragma unroll
-              for (int e = 0; e < 4; ++e) v[e] = gelu_tanh_f(v[e]);
-            }
-            if constexpr (EPI == VF_EPI_GELU_ERF_BF16) {
-#pragma unroll
-              for (int e = 0; e < 4; ++e) v[e] = gelu_erf_f(v[e]);
-            }
-            if (orow[i] >= 0) {
-              if constexpr (OUT_F32) {
-                float* o = reinterpret_cast<float*>(p.out) + orow[i] * p.ldo + cc;
-                if (vec) *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
-                else {
-#pragma unroll
-                  for (int e = 0; e < 4; ++e) if (cc + e < p.N) o[e] = v[e];
-                }
-              } else {
-                __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + orow[i] * p.ldo + cc;
-                if (vec) *reinterpret_cast<uint2*>(o) = make_uint2(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]));
-                else {
-#pragma unroll
-                  for (int e = 0; e < 4; ++e) if (cc + e < p.N) o[e] = __float2bfloat16_rn(v[e]);
-                }
+              for (int e = 0; e < 4; ++e) {
+                if (cc + e >= p.N) continue;
+                float v = xv[e] + (p.bias ? p.bias[cc + e] : 0.f);
+                if constexpr (EPI == VF_EPI_BIAS_RES_F32) v += reinterpret_cast<const float*>(rbase[i])[cc + e];
+                if constexpr (PATCH) { if (p.pos) v += p.pos[(long long)aux[i] * p.ld_pos + cc + e]; }
+                if constexpr (EPI == VF_EPI_GELU_TANH_BF16) v = gelu_tanh_f(v);
+                if constexpr (EPI == VF_EPI_GELU_ERF_BF16) v = gelu_erf_f(v);
+                if constexpr (OUT_F32) reinterpret_cast<float*>(obase[i])[cc + e] = v;
+                else reinterpret_cast<__nv_bfloat16*>(obase[i])[cc + e] = __float2bfloat16_rn(v);
               }
             }
           }
