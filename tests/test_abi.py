@@ -121,3 +121,24 @@ def test_product_never_imports_oracle():
     for p in (ROOT / "llm_quest_b200").rglob("*.py"):
         txt = p.read_text()
         assert "import oracle" not in txt and "from oracle" not in txt, p
+
+
+def test_shim_aliases_reference_module_paths():
+    import sys
+
+    import llm_quest_b200.shim as shim
+
+    saved = {k: sys.modules.get(k) for k in shim.ALIASES}
+    try:
+        names = shim.install()
+        import importlib
+
+        mod = importlib.import_module("llm_quest.qwen.qwen3_5.qwen3_5_vision_model")
+        assert mod.__name__ == "llm_quest_b200.qwen.qwen3_5.qwen3_5_vision_model" and hasattr(mod, "Qwen3_5VisionModel")
+        assert len(names) == len(shim.ALIASES)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v

@@ -15,10 +15,14 @@ with torch.inference_mode():
         m(x)
 torch.cuda.synchronize()
 PY
-if [ "$1" = "list" ]; then
+if true; then
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv python /tmp/one_step.py 2 > gpurun_out/ncu_list.log 2>&1
 echo "list exit=$?"
 fi
 ncu --set full --clock-control none --import-source on -k regex:gemm_kernel -s 54 -c 4 -o gpurun_out/prof_gemm -f python /tmp/one_step.py 2 > gpurun_out/ncu_gemm.log 2>&1
 echo "gemm exit=$?"
 ls -la gpurun_out/*.ncu-rep
+ncu --set full --clock-control none --import-source on -k regex:attention_kernel -s 13 -c 1 -o gpurun_out/prof_attn -f python /tmp/one_step.py 2 > gpurun_out/ncu_attn.log 2>&1
+echo "attn exit=$?"
+ncu --set full --clock-control none -k regex:layernorm_kernel -s 30 -c 1 -o gpurun_out/prof_ln -f python /tmp/one_step.py 2 > gpurun_out/ncu_ln.log 2>&1
+echo "ln exit=$?"
