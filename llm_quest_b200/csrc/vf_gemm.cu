@@ -304,6 +304,13 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
 
       if constexpr (EPI == VF_EPI_QKV_ROPE_BF16) {
         __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(p.out);
+        // cos/sin depend on (row, pair column) only: fetched once per tile, reused by every head
+        float4 cv[8], sv[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          cv[i] = __ldg(reinterpret_cast<const float4*>(p.rope_cos + (long long)aux[i] * 32) + cl);
+          sv[i] = __ldg(reinterpret_cast<const float4*>(p.rope_sin + (long long)aux[i] * 32) + cl);
+        }
 #pragma unroll 1
         for (int h = 0; h < BN / 64; ++h) {
           const int hc = col0 + h * 64;          // first column of this head
@@ -322,29 +329,14 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
             b1 = __ldg(reinterpret_cast<const float4*>(p.bias + hc) + cl);
             b2 = __ldg(reinterpret_cast<const float4*>(p.bias + hc + 32) + cl);
           }
-          // all table loads first (independent), then math, then predicated stores: no branches in the
-          // unrolled body, so the 8 rows of this lane overlap their latencies
-          float4 cv[8], sv[8];
-          if (rot) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              cv[i] = __ldg(reinterpret_cast<const float4*>(p.rope_cos + (long long)aux[i] * 32) + cl);
-              sv[i] = __ldg(reinterpret_cast<const float4*>(p.rope_sin + (long long)aux[i] * 32) + cl);
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              cv[i] = make_float4(1.f, 1.f, 1.f, 1.f);
-              sv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-          }
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int rr = rl + 4 * i;
             float4 x1 = read_staged(stA, rr), x2 = read_staged(stB, rr);
             x1.x += b1.x; x1.y += b1.y; x1.z += b1.z; x1.w += b1.w;
             x2.x += b2.x; x2.y += b2.y; x2.z += b2.z; x2.w += b2.w;
-            const float4 c = cv[i], sn = sv[i];
+            const float4 c = rot ? cv[i] : make_float4(1.f, 1.f, 1.f, 1.f);
+            const float4 sn = rot ? sv[i] : make_float4(0.f, 0.f, 0.f, 0.f);
             float4 y1, y2;
             y1.x = x1.x * c.x - x2.x * sn.x; y2.x = x2.x * c.x + x1.x * sn.x;
             y1.y = x1.y * c.y - x2.y * sn.y; y2.y = x2.y * c.y + x1.y * sn.y;
