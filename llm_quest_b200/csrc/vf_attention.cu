@@ -36,6 +36,7 @@
 #include "vf_common.cuh"
 
 #include <math.h>
+#include <stdlib.h>
 
 namespace vf {
 
@@ -84,6 +85,25 @@ __device__ __forceinline__ float fast_exp2(float x) {
 
 // Work items are ordered by decreasing cost: first every (b,h)'s full 4-tile block(s), the ragged last
 // block of each (b,h) at the end, so the static round-robin tail is short.
+// Boustrophedon ("snake") walk of the cost-sorted item list: round r hands items r*G .. r*G+G-1 to the
+// CTAs in ascending order when r is even and descending when r is odd, so the CTAs that received the
+// extra expensive item of a partial round get the cheap end of the next one (max load 38 instead of
+// 39 tile-units at S=784, B*H=768, G=148; the mean is 36.3).
+struct ItemIter {
+  int r, n;
+  __device__ explicit ItemIter(int n_items) : r(0), n(n_items) {}
+  __device__ __forceinline__ bool next(int& item) {
+    const int G = gridDim.x;
+    while (r * G < n) {
+      const int k = (r & 1) ? G - 1 - static_cast<int>(blockIdx.x) : static_cast<int>(blockIdx.x);
+      const int idx = r * G + k;
+      ++r;
+      if (idx < n) { item = idx; return true; }
+    }
+    return false;
+  }
+};
+
 __device__ __forceinline__ void decode_item(const AttnParams& p, int item, int& b, int& h, int& qb) {
   qb = item / p.n_bh;
   const int bh = item - qb * p.n_bh;
@@ -91,6 +111,11 @@ __device__ __forceinline__ void decode_item(const AttnParams& p, int item, int& 
   h = bh - b * p.H;
 }
 
+// FLAGS: bit 0 = per-sub-partition exp token (FIFO over the four softmax chains of a lane quarter),
+//        bit 1 = skip the exponentials of fully masked 16-key chunks of the ragged last key tile.
+constexpr int ATT_TOKEN = 1, ATT_TAILSKIP = 2;
+
+template <int FLAGS>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attention_kernel(const AttnParams p, const __grid_constant__ CUtensorMap tmQ,
                  const __grid_constant__ CUtensorMap tmKV) {
@@ -107,7 +132,8 @@ attention_kernel(const AttnParams p, const __grid_constant__ CUtensorMap tmQ,
   uint64_t* p_full = s_full + NQ;               // [NQ]
   uint64_t* o_full = p_full + NQ;               // [NQ]
   uint64_t* o_empty = o_full + NQ;              // [NQ]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_empty + NQ);
+  uint64_t* tok = o_empty + NQ;                 // [4 quarters][NQ tiles]: exp-phase token per SM sub-partition
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tok + 4 * NQ);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -131,7 +157,9 @@ attention_kernel(const AttnParams p, const __grid_constant__ CUtensorMap tmQ,
       mbar_init(&o_full[t], 1);
       mbar_init(&o_empty[t], 4);
     }
+    for (int i = 0; i < 4 * NQ; ++i) mbar_init(&tok[i], 1);
     fence_barrier_init();
+    for (int q = 0; q < 4; ++q) mbar_arrive(&tok[q * NQ]);   // tile 0 of every quarter owns the first turn
   }
   if (warp == MMA_WARP) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
@@ -150,7 +178,8 @@ attention_kernel(const AttnParams p, const __grid_constant__ CUtensorMap tmQ,
         int ks = 0, vs = 0;
         uint32_t kph = 0, vph = 0, qph = 0;   // qph: bit i = phase of q buffer i
         int qbuf = 0;
-        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        int item;
+        for (ItemIter it(p.n_items); it.next(item);) {
           int b, h, qb;
           decode_item(p, item, b, h, qb);
           const int row0 = b * p.S;
@@ -237,7 +266,8 @@ attention_kernel(const AttnParams p, const __grid_constant__ CUtensorMap tmQ,
         __syncwarp();
       };
 
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+      int item;
+      for (ItemIter it(p.n_items); it.next(item);) {
         int b, h, qb;
         decode_item(p, item, b, h, qb);
         int nt = (p.S - qb * (128 * NQ) + 127) / 128;  // query tiles of this item with >= 1 valid row
@@ -291,12 +321,15 @@ attention_kernel(const AttnParams p, const __grid_constant__ CUtensorMap tmQ,
     const uint32_t s_addr = tmem_base + lane_sel + t * 64;
     const uint32_t o_addr = tmem_base + lane_sel + 256 + t * 64;
     const int r_local = quarter * 32 + lane;
-    uint32_t sph = 0, oph = 0;
+    uint32_t sph = 0, oph = 0, tph = 0;
 
-    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+    int item;
+    for (ItemIter it(p.n_items); it.next(item);) {
       int b, h, qb;
       decode_item(p, item, b, h, qb);
       if (qb * (128 * NQ) + t * 128 >= p.S) continue;  // whole tile out of range (uniform per warp)
+      int nt_item = (p.S - qb * (128 * NQ) + 127) / 128;   // query tiles of this item (token ring size)
+      nt_item = nt_item > NQ ? NQ : nt_item;
       const int q_in_sample = qb * (128 * NQ) + t * 128 + r_local;
 
       float m = -INFINITY;   // running (possibly stale) row max, raw score units
@@ -344,18 +377,33 @@ attention_kernel(const AttnParams p, const __grid_constant__ CUtensorMap tmQ,
         }
         const float mb = m * p.scale_log2;
         float sum0 = 0.f, sum1 = 0.f;
+        if constexpr (FLAGS & ATT_TOKEN) {   // my turn on this sub-partition's MUFU
+          att_wait(&tok[quarter * NQ + t], tph); tph ^= 1;
+        }
 #pragma unroll
-        for (int c = 0; c < KT / 32; ++c) {
-          uint32_t pk[16];
+        for (int c = 0; c < KT / 16; ++c) {
+          uint32_t pk[8];
+          if (!(FLAGS & ATT_TAILSKIP) || c * 16 < valid) {   // warp-uniform
 #pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            const float p0 = fast_exp2(fmaf(s[c * 32 + 2 * e], p.scale_log2, -mb));
-            const float p1 = fast_exp2(fmaf(s[c * 32 + 2 * e + 1], p.scale_log2, -mb));
-            sum0 += p0;
-            sum1 += p1;
-            pk[e] = pack_bf16(p0, p1);
+            for (int e = 0; e < 8; ++e) {
+              const float p0 = fast_exp2(fmaf(s[c * 16 + 2 * e], p.scale_log2, -mb));
+              const float p1 = fast_exp2(fmaf(s[c * 16 + 2 * e + 1], p.scale_log2, -mb));
+              sum0 += p0;
+              sum1 += p1;
+              pk[e] = pack_bf16(p0, p1);
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) pk[e] = 0u;
           }
-          tmem_st_x16(s_addr + c * 16, pk);   // P_t (bf16 pairs) over the first 32 columns of S_t
+          tmem_st_x8(s_addr + c * 8, pk);   // P_t (bf16 pairs) over the first 32 columns of S_t
+          if constexpr (FLAGS & ATT_TOKEN) {
+            // hand the MUFU to the next chain once three quarters of this step's exponentials are
+            // issued (the rest overlaps the successor's first instructions)
+            if (c == KT / 16 - 2) {
+              if (lane == 0) mbar_arrive(&tok[quarter * NQ + (t + 1 == nt_item ? 0 : t + 1)]);
+            }
+          }
         }
         l += sum0 + sum1;
         tmem_st_wait();
@@ -432,16 +480,23 @@ extern "C" int vf_attention_fwd(const void* qkv, void* out, int32_t B, int32_t S
   e = encode_tmap(&tmKV, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, qkv, dims, strides, boxkv, CU_TENSOR_MAP_SWIZZLE_128B);
   if (e) return e;
 
-  static bool configured = false;
-  if (!configured) {
-    VF_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 AttnSmem::TOTAL));
-    configured = true;
+  // development switch: VF_ATTN_FLAGS selects a measured-slower variant for A/B runs
+  static int flags = -1;
+  if (flags < 0) {
+    const char* e_ = getenv("VF_ATTN_FLAGS");
+    flags = e_ ? atoi(e_) & 3 : 0;
+  }
+  using kern_t = void (*)(const AttnParams, const CUtensorMap, const CUtensorMap);
+  static const kern_t kerns[4] = {attention_kernel<0>, attention_kernel<1>, attention_kernel<2>, attention_kernel<3>};
+  static bool configured[4] = {false, false, false, false};
+  if (!configured[flags]) {
+    VF_CUDA(cudaFuncSetAttribute(kerns[flags], cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem::TOTAL));
+    configured[flags] = true;
   }
   const int sms = device_sm_count();
   VF_REQUIRE(sms > 0, VF_ERR_NO_DEVICE, "no CUDA device");
   const int grid = p.n_items < sms ? p.n_items : sms;
-  attention_kernel<<<grid, ATT_THREADS, AttnSmem::TOTAL, static_cast<cudaStream_t>(stream)>>>(p, tmQ, tmKV);
+  kerns[flags]<<<grid, ATT_THREADS, AttnSmem::TOTAL, static_cast<cudaStream_t>(stream)>>>(p, tmQ, tmKV);
   count_launch();
   VF_CUDA(cudaGetLastError());
   return VF_OK;

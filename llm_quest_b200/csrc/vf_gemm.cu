@@ -10,7 +10,7 @@
 //   * warp 1 / lane 0: tcgen05.mma issuer (cta_group::1, M=128, N=BN, K=16 per instruction),
 //     accumulators double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps the
 //     main loop of tile i+1;
-//   * warps 2..5: epilogue. tcgen05.ld 32x32b gives every thread one output row, so bias, GELU,
+//   * warps 2..9: epilogue. tcgen05.ld 32x32b gives every thread one output row, so bias, GELU,
 //     residual add, axial RoPE (pairs i / i+32 of a head live in the same thread) and the row
 //     remaps are all register-local.
 //   * patch-embedding mode gathers the A tile with ONE 5-D TMA box per stage straight from the
@@ -23,19 +23,18 @@
 #include "../../include/vfuse.h"
 
 #include <math.h>
+#include <stdlib.h>
 #include <type_traits>
 
 namespace vf {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int STAGES = 4;
-// warp0 TMA, warp1 MMA, then the epilogue warps: 4 for the QKV+RoPE epilogue (it needs two staging
-// blocks per warp), 8 for every other epilogue (two warps per TMEM lane quarter, each taking half of
-// the tile's columns — the epilogue is latency-bound, so the extra warps are what hides it).
+// warp0 TMA, warp1 MMA, then eight epilogue warps (two per TMEM lane quarter, each taking half of the
+// tile's columns — the epilogue is latency-bound, so the extra warps are what hides it).
 template <int EPI>
 struct EpiCfg {
-  static constexpr int WARPS = (EPI == VF_EPI_QKV_ROPE_BF16) ? 4 : 8;
+  static constexpr int WARPS = 8;
   static constexpr int THREADS = 64 + 32 * WARPS;
 };
 
@@ -66,10 +65,14 @@ struct GemmParams {
   long long ld_pos;
 };
 
-template <int BN>
+// CG = 1: one CTA per 128 x BN tile. CG = 2: a CTA pair (cta_group::2) per 256 x BN tile — each CTA stages
+// its own 128 A rows and HALF of the W tile, so a k-block costs 32 KB of L2->SM traffic per SM instead of
+// 48 KB (the 1-CTA kernel was capped by exactly that traffic, ~70 % tensor-pipe active) and six stages fit.
+template <int BN, int CG>
 struct SmemLayout {
+  static constexpr int STAGES = CG == 2 ? 6 : 4;
   static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int B_BYTES = (BN / CG) * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
   static constexpr int EPI_OFF = BAR_OFF + 256;            // 32 KB of 32x32 fp32 staging blocks for the epilogue warps
@@ -100,11 +103,13 @@ __device__ __forceinline__ float gelu_erf_f(float x) {
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
 }
 
-template <int EPI, int BN, bool PATCH>
+template <int EPI, int BN, bool PATCH, int CG>
 __global__ void __launch_bounds__(EpiCfg<EPI>::THREADS, 1)
 gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
             const __grid_constant__ CUtensorMap tmB) {
-  using L = SmemLayout<BN>;
+  static_assert(CG == 1 || (CG == 2 && BN == 256 && !PATCH), "CTA pairs: 256-wide tiles, plain A operand");
+  using L = SmemLayout<BN, CG>;
+  constexpr int STAGES = L::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
@@ -115,7 +120,10 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_tiles = p.num_m_blk * p.num_n_blk;
+  // tile walk: a "tile" is BM*CG rows x BN columns; CTA `rank` of a pair owns its rows [rank*BM, +BM)
+  const int rank = CG == 2 ? static_cast<int>(cluster_ctarank()) : 0;
+  const int num_tiles = ((p.num_m_blk + CG - 1) / CG) * p.num_n_blk;
+  const int tile0 = blockIdx.x / CG, tile_step = gridDim.x / CG;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -126,13 +134,17 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], EpiCfg<EPI>::WARPS);  // one arrival per epilogue warp
+      mbar_init(&tempty_bar[a], EpiCfg<EPI>::WARPS * CG);  // one arrival per epilogue warp (of both CTAs)
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<2 * BN>(tmem_slot);
+  if (warp == 1) {
+    if constexpr (CG == 2) tmem_alloc_pair<2 * BN>(tmem_slot);
+    else tmem_alloc<2 * BN>(tmem_slot);
+  }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();   // barrier inits + TMEM of both CTAs visible to the pair
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -141,9 +153,9 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
         const int n_blk = tile % p.num_n_blk;
-        const int m_blk = tile / p.num_n_blk;
+        const int m_blk = (tile / p.num_n_blk) * CG + rank;
         int pc2 = 0, pc3 = 0, pimg = 0;  // patch mode: pw0, ph0, (b*C)*T + t'*tp
         if (PATCH) {
           int t = m_blk;
@@ -159,7 +171,7 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
           wait_or_trap(&empty_bar[stage], phase ^ 1);
           uint8_t* a_dst = smem + stage * L::STAGE_BYTES;
           uint8_t* b_dst = a_dst + L::A_BYTES;
-          mbar_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+          if (rank == 0) mbar_expect_tx(&full_bar[stage], L::STAGE_BYTES * CG);   // the pair's bytes land on the leader
           if (PATCH) {
             // K index = ((c*tp + dt)*P + py)*P + px ; one 64-wide k-block = (64/P) pixel rows.
             const int rows_per_kb = BK / p.P;
@@ -168,23 +180,26 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
             const int py0 = (kb % kb_per_plane) * rows_per_kb;
             const int c = plane / p.tp, dt = plane % p.tp;
             tma_load_5d(a_dst, &tmA, &full_bar[stage], 0, pc2, py0, pc3, pimg + c * p.T + dt);
+          } else if (CG == 2) {
+            tma_load_2d_pair(a_dst, &tmA, &full_bar[stage], kb * BK, m_blk * BM);
           } else {
             tma_load_2d(a_dst, &tmA, &full_bar[stage], kb * BK, m_blk * BM);
           }
-          tma_load_2d(b_dst, &tmB, &full_bar[stage], kb * BK, n_blk * BN);
+          if (CG == 2) tma_load_2d_pair(b_dst, &tmB, &full_bar[stage], kb * BK, n_blk * BN + rank * (BN / 2));
+          else tma_load_2d(b_dst, &tmB, &full_bar[stage], kb * BK, n_blk * BN);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, 0, 0);
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM * CG, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
         wait_or_trap(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
@@ -202,18 +217,23 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k) {
               // advance 16 bf16 = 32 B inside the 128 B swizzle atom: +2 in the (addr>>4) field
-              umma_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+              if (CG == 2) umma_ss_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+              else umma_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
             }
           }
-          umma_commit(&empty_bar[stage]);  // smem slot is free once these MMAs retire
+          // smem slot is free (in both CTAs of a pair) once these MMAs retire
+          if (CG == 2) umma_commit_pair(&empty_bar[stage]);
+          else umma_commit(&empty_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull_bar[acc]);      // accumulator complete
+        // accumulator complete (each CTA of a pair drains its own 128 rows)
+        if (CG == 2) umma_commit_pair(&tfull_bar[acc]);
+        else umma_commit(&tfull_bar[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    // ------------------------------------------------------------------ epilogue (warps 2..9)
     // tcgen05.ld hands every thread one accumulator ROW; global memory wants warps to touch whole
     // 128-byte lines. Each warp therefore transposes 32x32 fp32 blocks through a private, XOR-swizzled
     // (conflict-free) shared-memory buffer and does all epilogue math + I/O in the coalesced mapping:
@@ -225,7 +245,6 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
     constexpr int COLS_PER_WARP = BN / (EW / 4);      // columns of the tile this warp drains
     const int chalf = (warp - 2) >> 2;                // 0, or 0/1 with eight warps
     const uint32_t stA = smem_u32(smem + L::EPI_OFF + (warp - 2) * (32768 / EW));
-    const uint32_t stB = stA + 4096;                  // second block: RoPE epilogue only
     const int cl = lane & 7;       // 16-byte column group inside a 32-column block
     const int rl = lane >> 3;      // row offset inside a group of 4 rows
     int acc = 0;
@@ -249,10 +268,30 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
       return v;
     };
 
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    // Residual epilogue: the fp32 residual slab of a tile (128 KB) is pulled into L2 one tile ahead, while
+    // the tensor pipe is still busy with the current one, so the epilogue's loads are L2 hits instead of
+    // serialised DRAM round trips (measured: the proj GEMM, K=768, was bound by exactly that latency).
+    auto prefetch_res = [&](int tile) {
+      if constexpr (EPI == VF_EPI_BIAS_RES_F32 && !PATCH) {
+        if (tile < num_tiles && p.grp_rows == 0) {
+          const int m = ((tile / p.num_n_blk) * CG + rank) * BM + quarter * 32 + lane;
+          const int c0 = (tile % p.num_n_blk) * BN + chalf * COLS_PER_WARP;
+          if (m < p.M) {
+            const char* rp = reinterpret_cast<const char*>(p.res + (long long)m * p.ldr + c0);
+#pragma unroll
+            for (int i = 0; i < COLS_PER_WARP * 4 / 128; ++i)
+              if (c0 + i * 32 < p.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + i * 128));
+          }
+        }
+      }
+    };
+    prefetch_res(tile0);
+
+    for (int tile = tile0; tile < num_tiles; tile += tile_step) {
       const int n_blk = tile % p.num_n_blk;
-      const int m_blk = tile / p.num_n_blk;
+      const int m_blk = (tile / p.num_n_blk) * CG + rank;
       const int col0 = n_blk * BN;
+      prefetch_res(tile + tile_step);
 
       // ---- output row (or -1) of the 8 rows this lane touches: rows r0, r0+4, ..., r0+28 of the tile.
       // One integer division per tile at most; the other rows follow incrementally.
@@ -312,15 +351,23 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
           sv[i] = __ldg(reinterpret_cast<const float4*>(p.rope_sin + (long long)aux[i] * 32) + cl);
         }
 #pragma unroll 1
-        for (int h = 0; h < BN / 64; ++h) {
-          const int hc = col0 + h * 64;          // first column of this head
-          uint32_t r1[32], r2[32];
-          tmem_ld_x32(t_row + h * 64, r1);
-          tmem_ld_x32(t_row + h * 64 + 32, r2);
+        for (int hh = 0; hh < COLS_PER_WARP / 64; ++hh) {
+          const int hc = col0 + chalf * COLS_PER_WARP + hh * 64;   // first column of this head
+          // The rotation pairs column i with i+32 of the same row. Both halves go through ONE staging
+          // block: the first half is parked in registers (coalesced mapping) while the second is staged.
+          uint32_t r[32];
+          tmem_ld_x32(t_row + hh * 64, r);
           tmem_ld_wait();
           __syncwarp();                          // previous head fully consumed by all lanes
-          stage_row(stA, r1);
-          stage_row(stB, r2);
+          stage_row(stA, r);
+          tmem_ld_x32(t_row + hh * 64 + 32, r);  // second half in flight while the first is read back
+          __syncwarp();
+          float4 x1s[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) x1s[i] = read_staged(stA, rl + 4 * i);
+          tmem_ld_wait();
+          __syncwarp();
+          stage_row(stA, r);
           __syncwarp();
           if (hc >= p.N) continue;
           const bool rot = hc < p.rope_cols;
@@ -332,7 +379,7 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int rr = rl + 4 * i;
-            float4 x1 = read_staged(stA, rr), x2 = read_staged(stB, rr);
+            float4 x1 = x1s[i], x2 = read_staged(stA, rr);
             x1.x += b1.x; x1.y += b1.y; x1.z += b1.z; x1.w += b1.w;
             x2.x += b2.x; x2.y += b2.y; x2.z += b2.z; x2.w += b2.w;
             const float4 c = rot ? cv[i] : make_float4(1.f, 1.f, 1.f, 1.f);
@@ -444,53 +491,71 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
       // release the accumulator buffer (all tcgen05.ld of this warp have completed)
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (lane == 0) {
+        if (CG == 2) mbar_arrive_leader(&tempty_bar[acc]);   // the leader's MMA warp reuses the buffer pair-wide
+        else mbar_arrive(&tempty_bar[acc]);
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();   // the peer may still be reading this CTA's smem / TMEM
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<2 * BN>(tmem_base);
+    if constexpr (CG == 2) tmem_dealloc_pair<2 * BN>(tmem_base);
+    else tmem_dealloc<2 * BN>(tmem_base);
   }
 }
 
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-template <int EPI, int BN, bool PATCH = false>
+template <int EPI, int BN, bool PATCH = false, int CG = 1>
 static int launch_gemm(const GemmParams& p, const CUtensorMap& tmA, const CUtensorMap& tmB,
                        cudaStream_t stream) {
-  using L = SmemLayout<BN>;
+  using L = SmemLayout<BN, CG>;
   static bool configured = false;
-  auto kfn = gemm_kernel<EPI, BN, PATCH>;
+  auto kfn = gemm_kernel<EPI, BN, PATCH, CG>;
   if (!configured) {
     VF_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     configured = true;
   }
   const int sms = device_sm_count();
   VF_REQUIRE(sms > 0, VF_ERR_NO_DEVICE, "no CUDA device");
-  const int tiles = p.num_m_blk * p.num_n_blk;
-  const int grid = tiles < sms ? tiles : sms;
-  kfn<<<grid, EpiCfg<EPI>::THREADS, L::TOTAL, stream>>>(p, tmA, tmB);
+  const int tiles = ((p.num_m_blk + CG - 1) / CG) * p.num_n_blk;
+  const int slots = sms / CG;                       // persistent: one CTA (pair) per SM (pair)
+  const int grid = (tiles < slots ? tiles : slots) * CG;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(EpiCfg<EPI>::THREADS);
+  cfg.dynamicSmemBytes = L::TOTAL;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  VF_CUDA(cudaLaunchKernelEx(&cfg, kfn, p, tmA, tmB));
   count_launch();
   VF_CUDA(cudaGetLastError());
   return VF_OK;
 }
 
-template <int BN>
+template <int BN, int CG>
 static int dispatch_epi(int mode, const GemmParams& p, const CUtensorMap& a, const CUtensorMap& b,
                         cudaStream_t s) {
   switch (mode) {
-    case VF_EPI_BIAS_BF16: return launch_gemm<VF_EPI_BIAS_BF16, BN>(p, a, b, s);
-    case VF_EPI_BIAS_F32: return launch_gemm<VF_EPI_BIAS_F32, BN>(p, a, b, s);
-    case VF_EPI_BIAS_RES_F32: return launch_gemm<VF_EPI_BIAS_RES_F32, BN>(p, a, b, s);
-    case VF_EPI_GELU_TANH_BF16: return launch_gemm<VF_EPI_GELU_TANH_BF16, BN>(p, a, b, s);
-    case VF_EPI_GELU_ERF_BF16: return launch_gemm<VF_EPI_GELU_ERF_BF16, BN>(p, a, b, s);
-    case VF_EPI_QKV_ROPE_BF16: return launch_gemm<VF_EPI_QKV_ROPE_BF16, BN>(p, a, b, s);
-    case VF_EPI_SCATTER_BF16: return launch_gemm<VF_EPI_SCATTER_BF16, BN>(p, a, b, s);
+    case VF_EPI_BIAS_BF16: return launch_gemm<VF_EPI_BIAS_BF16, BN, false, CG>(p, a, b, s);
+    case VF_EPI_BIAS_F32: return launch_gemm<VF_EPI_BIAS_F32, BN, false, CG>(p, a, b, s);
+    case VF_EPI_BIAS_RES_F32: return launch_gemm<VF_EPI_BIAS_RES_F32, BN, false, CG>(p, a, b, s);
+    case VF_EPI_GELU_TANH_BF16: return launch_gemm<VF_EPI_GELU_TANH_BF16, BN, false, CG>(p, a, b, s);
+    case VF_EPI_GELU_ERF_BF16: return launch_gemm<VF_EPI_GELU_ERF_BF16, BN, false, CG>(p, a, b, s);
+    case VF_EPI_QKV_ROPE_BF16: return launch_gemm<VF_EPI_QKV_ROPE_BF16, BN, false, CG>(p, a, b, s);
+    case VF_EPI_SCATTER_BF16: return launch_gemm<VF_EPI_SCATTER_BF16, BN, false, CG>(p, a, b, s);
     default: break;
   }
   set_last_error("vf_gemm_bf16: unknown epilogue mode %d", mode);
@@ -552,6 +617,15 @@ extern "C" int vf_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t l
   p.dst_rows = ep->dst_rows;
   p.vec_ok = vec_ok ? 1 : 0;
 
+  // CTA pairs for every 256-wide problem with at least one full pair of row blocks per SM pair
+  // (VF_GEMM_CG=1 forces the single-CTA kernel: development A/B switch)
+  static int cg_env = -1;
+  if (cg_env < 0) {
+    const char* e_ = getenv("VF_GEMM_CG");
+    cg_env = e_ ? atoi(e_) : 2;
+  }
+  const int cg = (bn == 256 && cg_env == 2 && p.num_m_blk >= 2) ? 2 : 1;
+
   CUtensorMap tmA, tmB;
   {
     uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
@@ -564,14 +638,15 @@ extern "C" int vf_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t l
   {
     uint64_t dims[2] = {(uint64_t)K, (uint64_t)N};
     uint64_t strides[1] = {(uint64_t)ldw * 2};
-    uint32_t box[2] = {BK, (uint32_t)bn};
+    uint32_t box[2] = {BK, (uint32_t)(bn / cg)};
     int e = encode_tmap(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, W, dims, strides, box,
                         CU_TENSOR_MAP_SWIZZLE_128B);
     if (e) return e;
   }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  return bn == 256 ? dispatch_epi<256>(ep->mode, p, tmA, tmB, s)
-                   : dispatch_epi<128>(ep->mode, p, tmA, tmB, s);
+  if (cg == 2) return dispatch_epi<256, 2>(ep->mode, p, tmA, tmB, s);
+  return bn == 256 ? dispatch_epi<256, 1>(ep->mode, p, tmA, tmB, s)
+                   : dispatch_epi<128, 1>(ep->mode, p, tmA, tmB, s);
 }
 
 extern "C" int vf_patch_embed(const void* pixels, int32_t B, int32_t C, int32_t T, int32_t H,
