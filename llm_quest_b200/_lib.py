@@ -266,11 +266,12 @@ def rope_apply(x, cos, sin, position_ids=None):
     xc = x.contiguous()
     out = torch.empty_like(xc)
     pid = None if position_ids is None else position_ids.to(torch.int64).contiguous()
-    check(
-        lib().vf_rope_apply(xc.data_ptr(), out.data_ptr(), _DT[x.dtype], B, H, S, hd, cos.data_ptr(), sin.data_ptr(),
-                            cos.shape[-1], cos.shape[0], _p(pid), _stream()),
-        "vf_rope_apply",
-    )
+    with _timed("rope_apply", bytes=2.0 * xc.numel() * xc.element_size()):
+        check(
+            lib().vf_rope_apply(xc.data_ptr(), out.data_ptr(), _DT[x.dtype], B, H, S, hd, cos.data_ptr(), sin.data_ptr(),
+                                cos.shape[-1], cos.shape[0], _p(pid), _stream()),
+            "vf_rope_apply",
+        )
     return out
 
 
@@ -281,12 +282,13 @@ def mrope_apply(x, cos, sin, position_ids, mrope_section, norm_weight=None, norm
     out = torch.empty_like(xc)
     pid = position_ids.to(torch.int64).contiguous()
     st, sh, sw = (int(v) for v in mrope_section)
-    check(
-        lib().vf_mrope_apply(xc.data_ptr(), out.data_ptr(), _DT[x.dtype], B, H, S, hd, cos.data_ptr(), sin.data_ptr(),
-                             cos.shape[-1], cos.shape[0], pid.data_ptr(), st, sh, sw, _p(norm_weight),
-                             float(norm_eps), _stream()),
-        "vf_mrope_apply",
-    )
+    with _timed("mrope_apply", bytes=2.0 * xc.numel() * xc.element_size() + 8.0 * pid.numel()):
+        check(
+            lib().vf_mrope_apply(xc.data_ptr(), out.data_ptr(), _DT[x.dtype], B, H, S, hd, cos.data_ptr(), sin.data_ptr(),
+                                 cos.shape[-1], cos.shape[0], pid.data_ptr(), st, sh, sw, _p(norm_weight),
+                                 float(norm_eps), _stream()),
+            "vf_mrope_apply",
+        )
     return out
 
 
@@ -298,11 +300,12 @@ def mrope_position_ids(input_ids, image_mask, image_token_id, feeds_cpu, merge):
     mask = None if image_mask is None else image_mask.to(torch.uint8).contiguous()
     feeds = feeds_cpu.to(device="cpu", dtype=torch.int64).contiguous()
     out = torch.empty((3, b, seq), dtype=torch.int64, device=input_ids.device)
-    check(
-        lib().vf_mrope_position_ids(ids.data_ptr(), _p(mask), int(image_token_id), feeds.data_ptr(), feeds.shape[0],
-                                    int(merge), b, seq, out.data_ptr(), _stream()),
-        "vf_mrope_position_ids",
-    )
+    with _timed("mrope_position_ids", bytes=32.0 * b * seq):   # read ids (8 B), write 3 axes (24 B)
+        check(
+            lib().vf_mrope_position_ids(ids.data_ptr(), _p(mask), int(image_token_id), feeds.data_ptr(), feeds.shape[0],
+                                        int(merge), b, seq, out.data_ptr(), _stream()),
+            "vf_mrope_position_ids",
+        )
     return out
 
 
@@ -317,11 +320,12 @@ def fuse_scan(input_ids, image_mask, image_token_id, inv_cap=0):
     count = torch.empty(1, dtype=torch.int32, device=ids.device)
     inv = torch.empty(inv_cap, dtype=torch.int32, device=ids.device) if inv_cap > 0 else None
     scratch = torch.empty(n // 1024 + 1024, dtype=torch.int32, device=ids.device)
-    check(
-        lib().vf_fuse_scan(ids.data_ptr(), _p(mask), int(image_token_id), n, row_map.data_ptr(), count.data_ptr(),
-                           _p(inv), inv_cap, scratch.data_ptr(), _stream()),
-        "vf_fuse_scan",
-    )
+    with _timed("fuse_scan", bytes=12.0 * n + 4.0 * inv_cap):   # read ids (8 B), write rank (4 B) + inverse map
+        check(
+            lib().vf_fuse_scan(ids.data_ptr(), _p(mask), int(image_token_id), n, row_map.data_ptr(), count.data_ptr(),
+                               _p(inv), inv_cap, scratch.data_ptr(), _stream()),
+            "vf_fuse_scan",
+        )
     return row_map, count, inv
 
 
@@ -334,11 +338,13 @@ def embed_gather_scatter(input_ids, table, vision, row_map, out, skip_vision=Fal
     if vision is not None:
         assert vision.is_contiguous() and vision.shape[-1] == D
         n_vis, vd = vision.numel() // D, _DT[vision.dtype]
-    check(
-        lib().vf_embed_gather_scatter(ids.data_ptr(), table.data_ptr(), table.shape[0], D, _p(vision), vd, n_vis,
-                                      _p(row_map), out.data_ptr(), ids.numel(), int(skip_vision), _stream()),
-        "vf_embed_gather_scatter",
-    )
+    rows_moved = ids.numel() - (n_vis if skip_vision else 0)   # placeholder rows are skipped in skip mode
+    with _timed("embed_gather_scatter", bytes=rows_moved * D * 4.0 + ids.numel() * 12.0):
+        check(
+            lib().vf_embed_gather_scatter(ids.data_ptr(), table.data_ptr(), table.shape[0], D, _p(vision), vd, n_vis,
+                                          _p(row_map), out.data_ptr(), ids.numel(), int(skip_vision), _stream()),
+            "vf_embed_gather_scatter",
+        )
     return out
 
 
@@ -349,7 +355,8 @@ def to_bf16(x):
     assert x.dtype == torch.float32
     xc = x.contiguous()
     out = torch.empty(xc.shape, dtype=torch.bfloat16, device=x.device)
-    check(lib().vf_cast_f32_to_bf16(xc.data_ptr(), out.data_ptr(), xc.numel(), _stream()), "vf_cast_f32_to_bf16")
+    with _timed("cast", bytes=6.0 * xc.numel()):
+        check(lib().vf_cast_f32_to_bf16(xc.data_ptr(), out.data_ptr(), xc.numel(), _stream()), "vf_cast_f32_to_bf16")
     return out
 
 
@@ -360,5 +367,6 @@ def to_f32(x):
     assert x.dtype == torch.bfloat16
     xc = x.contiguous()
     out = torch.empty(xc.shape, dtype=torch.float32, device=x.device)
-    check(lib().vf_cast_bf16_to_f32(xc.data_ptr(), out.data_ptr(), xc.numel(), _stream()), "vf_cast_bf16_to_f32")
+    with _timed("cast", bytes=6.0 * xc.numel()):
+        check(lib().vf_cast_bf16_to_f32(xc.data_ptr(), out.data_ptr(), xc.numel(), _stream()), "vf_cast_bf16_to_f32")
     return out

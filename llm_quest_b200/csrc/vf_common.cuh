@@ -249,7 +249,10 @@ __device__ __forceinline__ void cluster_sync_all() {   // every thread of every 
 __device__ __forceinline__ uint32_t leader_smem_u32(const void* p) { return smem_u32(p) & 0xFEFFFFFFu; }
 
 __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(leader_smem_u32(bar)) : "memory");
+  // relaxed: the arrival only publishes "my tcgen05.ld of this accumulator are done" (ordered by the tcgen05
+  // fence); a release at cluster scope would drain every outstanding global store first (MEMBAR, ~10 % of
+  // the residual epilogue's stall samples)
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(leader_smem_u32(bar)) : "memory");
 }
 // TMA load issued by either CTA of a pair into ITS OWN shared memory; the bytes are accounted on the
 // LEADER's mbarrier.
