@@ -117,6 +117,10 @@ int vf_patch_embed(const void* pixels, int32_t B, int32_t C, int32_t T, int32_t 
  * ------------------------------------------------------------------------------------------- */
 int vf_attention_fwd(const void* qkv, void* out, int32_t B, int32_t S, int32_t H, float scale,
                      void* stream);
+/* Diagnosis only: with a trace build selected (VF_ATTN_FLAGS bit 1) block 0 of every following
+ * vf_attention_fwd writes clock64 stamps into buf — uint64 [20 chains][n_steps][8] — for the key steps
+ * [first_step, first_step + n_steps) of each softmax chain / MMA walker. buf = NULL switches it off. */
+int vf_attention_set_trace(void* buf, int32_t first_step, int32_t n_steps);
 
 /* ---------------------------------------------------------------------------------------------
  * LayerNorm over the last dim, fp32 or bf16 in, bf16 or fp32 out, fp32 statistics.

@@ -49,6 +49,16 @@ constexpr int MMA_WARP = NQ * 4 + 1;     // warps 17, 18 (sub-partitions 1, 2): 
 constexpr int Q_TILE_BYTES = 128 * 64 * 2;  // 16 KB
 constexpr int KV_TILE_BYTES = KT * 64 * 2;  // 8 KB
 
+// bit 1 = trace build: block 0 records clock64 stamps per chain and key step into AttnParams::trace
+// (vf_attention_set_trace); diagnosis only, never the default.
+constexpr int ATT_TRACE = 2;
+// bit 2 = lean softmax step: packed f32x2 arithmetic (FFMA2 / FADD2: the softmax warps are bound by issue
+// slots, not only by the MUFU) and NO per-step row max: the max of the first key tile stays the reference
+// and a step is redone with a fresh max only when its row sum shows that an exponent ran away (> 2^60).
+// bf16 P and fp32 O/l keep full relative precision at any common scale, so the result is unchanged.
+constexpr int ATT_LEAN = 4;
+constexpr int TRACE_STAMPS = 8;
+
 struct AttnParams {
   int B, S, H;
   int n_qblk;      // ceil(S / (128*NQ))
@@ -56,6 +66,9 @@ struct AttnParams {
   int n_items;     // B * H * n_qblk
   int n_bh;        // B * H
   float scale_log2;
+  unsigned long long* trace;   // [20 rows][trace_n steps][TRACE_STAMPS] clock64 stamps of block 0, or nullptr
+  int trace_first, trace_n;
+  int stagger;     // any-order walkers: one-time start offset between the four chains, in cycles (0 = none)
   __nv_bfloat16* out;
 };
 
@@ -75,6 +88,35 @@ __device__ __forceinline__ void att_wait(uint64_t* bar, uint32_t parity) {
       __trap();
     }
   }
+}
+
+template <int FLAGS>
+__device__ __forceinline__ void att_trace(const AttnParams& p, int row, int step, int k) {
+  if constexpr (FLAGS & ATT_TRACE) {
+    if (p.trace && blockIdx.x == 0 && (threadIdx.x & 31) == 0) {
+      const int i = step - p.trace_first;
+      if (i >= 0 && i < p.trace_n) p.trace[(static_cast<long long>(row) * p.trace_n + i) * TRACE_STAMPS + k] = clock64();
+    }
+  }
+}
+
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
 }
 
 __device__ __forceinline__ float fast_exp2(float x) {
@@ -111,9 +153,14 @@ __device__ __forceinline__ void decode_item(const AttnParams& p, int item, int& 
   h = bh - b * p.H;
 }
 
-// FLAGS: bit 0 = per-sub-partition exp token (FIFO over the four softmax chains of a lane quarter),
-//        bit 1 = skip the exponentials of fully masked 16-key chunks of the ragged last key tile.
-constexpr int ATT_TOKEN = 1, ATT_TAILSKIP = 2;
+// FLAGS: bit 0 = the MMA warps walk their two query tiles as INDEPENDENT chains (any-order issue: whichever
+// tile's P is ready is served first) instead of tile 0 then tile 1 of every key step. The in-order walk
+// couples the softmax chains: a chain that runs ahead has to wait for its pair, all four end up in lockstep,
+// compute their exponentials at the same time (sharing the MUFU) and wait for the tensor core at the same
+// time (MUFU idle). Tried and measured slower (round 1): a FIFO token that serialises the exp phases per
+// sub-partition (hand-off latency eats the gain: 2675 vs 2459 us at S=6272), and skipping the exponentials
+// of masked 16-key chunks with a branch inside the unrolled loop (breaks the interleaving).
+constexpr int ATT_ANYORDER = 1;
 
 template <int FLAGS>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
@@ -132,8 +179,7 @@ attention_kernel(const AttnParams p, const __grid_constant__ CUtensorMap tmQ,
   uint64_t* p_full = s_full + NQ;               // [NQ]
   uint64_t* o_full = p_full + NQ;               // [NQ]
   uint64_t* o_empty = o_full + NQ;              // [NQ]
-  uint64_t* tok = o_empty + NQ;                 // [4 quarters][NQ tiles]: exp-phase token per SM sub-partition
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tok + 4 * NQ);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_empty + NQ);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -143,13 +189,13 @@ attention_kernel(const AttnParams p, const __grid_constant__ CUtensorMap tmQ,
     tma_prefetch_desc(&tmKV);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&q_full[i], 1);
-      mbar_init(&q_empty[i], 2);   // both MMA issuers
+      mbar_init(&q_empty[i], (FLAGS & ATT_ANYORDER) ? NQ : 2);   // every tile walker / both MMA issuers
     }
     for (int s = 0; s < KV_STAGES; ++s) {
       mbar_init(&k_full[s], 1);
-      mbar_init(&k_empty[s], 2);
+      mbar_init(&k_empty[s], (FLAGS & ATT_ANYORDER) ? NQ : 2);
       mbar_init(&v_full[s], 1);
-      mbar_init(&v_empty[s], 2);
+      mbar_init(&v_empty[s], (FLAGS & ATT_ANYORDER) ? NQ : 2);
     }
     for (int t = 0; t < NQ; ++t) {
       mbar_init(&s_full[t], 1);
@@ -157,9 +203,7 @@ attention_kernel(const AttnParams p, const __grid_constant__ CUtensorMap tmQ,
       mbar_init(&o_full[t], 1);
       mbar_init(&o_empty[t], 4);
     }
-    for (int i = 0; i < 4 * NQ; ++i) mbar_init(&tok[i], 1);
     fence_barrier_init();
-    for (int q = 0; q < 4; ++q) mbar_arrive(&tok[q * NQ]);   // tile 0 of every quarter owns the first turn
   }
   if (warp == MMA_WARP) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
@@ -171,7 +215,7 @@ attention_kernel(const AttnParams p, const __grid_constant__ CUtensorMap tmQ,
     // loader / MMA / idle warps: hand registers to the softmax warpgroups. Budget: the CTA owns
     // 640 x 96 registers at launch; 128 x 56 + 512 x 104 fits inside that pool (setmaxnreg.inc can
     // only draw from what the CTA already holds — asking for more deadlocks the warpgroup).
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
     if (warp == LOADER_WARP) {
       // ---------------------------------------------------------------- TMA loader
       if (lane == 0) {
@@ -222,9 +266,9 @@ attention_kernel(const AttnParams p, const __grid_constant__ CUtensorMap tmQ,
       int qbuf = 0;
       uint32_t pph = 0, oeph = 0;   // bit t = phase of p_full[t] / o_empty[t]
 
-      auto issue_s = [&](int t, int kstage) {
+      auto issue_s_q = [&](int t, int kstage, int qb_) {
         if (elect_one()) {
-          const uint64_t a_ = q_desc + (qbuf * NQ + t) * QT_DESC;
+          const uint64_t a_ = q_desc + (qb_ * NQ + t) * QT_DESC;
           const uint64_t b_ = k_desc + kstage * KVT_DESC;
 #pragma unroll
           for (int k_ = 0; k_ < 4; ++k_)      // head_dim 64 = 4 x K16
@@ -233,25 +277,15 @@ attention_kernel(const AttnParams p, const __grid_constant__ CUtensorMap tmQ,
         }
         __syncwarp();
       };
-      auto issue_pv = [&](int t, int vstage, bool accumulate) {
-        if (elect_one()) {
-          const uint64_t b_ = v_desc + vstage * KVT_DESC;
-#pragma unroll
-          for (int k_ = 0; k_ < KT / 16; ++k_)  // 16 keys per MMA: 8 TMEM columns of bf16x2 / 16 V rows
-            umma_ts(tmem_base + 256 + t * 64, tmem_base + t * 64 + k_ * 8, b_ + k_ * (2048 >> 4), idesc_o,
-                    accumulate || k_ != 0);
-        }
-        __syncwarp();
-      };
-      auto issue_pv_s = [&](int t, int vstage, bool accumulate, bool with_s, int kstage) {
+      auto issue_pv_s_q = [&](int t, int vstage, bool accumulate, bool with_s, int kstage, int qb_) {
         if (elect_one()) {
           const uint64_t bv_ = v_desc + vstage * KVT_DESC;
 #pragma unroll
-          for (int k_ = 0; k_ < KT / 16; ++k_)
+          for (int k_ = 0; k_ < KT / 16; ++k_)  // 16 keys per MMA: 8 TMEM columns of bf16x2 / 16 V rows
             umma_ts(tmem_base + 256 + t * 64, tmem_base + t * 64 + k_ * 8, bv_ + k_ * (2048 >> 4), idesc_o,
                     accumulate || k_ != 0);
           if (with_s) {
-            const uint64_t a_ = q_desc + (qbuf * NQ + t) * QT_DESC;
+            const uint64_t a_ = q_desc + (qb_ * NQ + t) * QT_DESC;
             const uint64_t bk_ = k_desc + kstage * KVT_DESC;
 #pragma unroll
             for (int k_ = 0; k_ < 4; ++k_)
@@ -261,11 +295,112 @@ attention_kernel(const AttnParams p, const __grid_constant__ CUtensorMap tmQ,
         }
         __syncwarp();
       };
+      auto issue_s = [&](int t, int kstage) { issue_s_q(t, kstage, qbuf); };
+      auto issue_pv_s = [&](int t, int vstage, bool accumulate, bool with_s, int kstage) {
+        issue_pv_s_q(t, vstage, accumulate, with_s, kstage, qbuf);
+      };
       auto commit = [&](uint64_t* bar) {
         if (elect_one()) umma_commit(bar);
         __syncwarp();
       };
 
+      if constexpr (FLAGS & ATT_ANYORDER) {
+        // ---- two independent tile walkers, served in whatever order their barriers complete
+        struct Walk {
+          ItemIter it;
+          int t, nt, j, qbuf, ks, vs;          // j = -1: S(t,0) of the current item is the next action
+          uint32_t qph, kph, vph, pph, oeph;   // qph: bit i = phase of q buffer i
+          bool done;
+          int gstep;
+          __device__ Walk(int n_items) : it(n_items), gstep(0) {}
+        };
+        auto next_item = [&](Walk& w) {
+          int item;
+          if (!w.it.next(item)) { w.done = true; return; }
+          int b_, h_, qb_;
+          decode_item(p, item, b_, h_, qb_);
+          int nt = (p.S - qb_ * (128 * NQ) + 127) / 128;
+          w.nt = nt > NQ ? NQ : nt;
+          w.j = -1;
+        };
+        // one action of walker w if everything it needs has arrived; never blocks
+        auto advance = [&](Walk& w) -> bool {
+          const int t = w.t;
+          const bool mine = t < w.nt;          // tiles beyond the item's last query tile only recycle K/V slots
+          if (w.j < 0) {
+            if (!mbar_try_wait(&q_full[w.qbuf], (w.qph >> w.qbuf) & 1)) return false;
+            if (!mbar_try_wait(&k_full[w.ks], w.kph)) return false;
+            tc_fence_after();
+            if (mine) issue_s_q(t, w.ks, w.qbuf);
+            commit(&k_empty[w.ks]);
+            if (p.n_kt == 1) commit(&q_empty[w.qbuf]);
+            if (++w.ks == KV_STAGES) { w.ks = 0; w.kph ^= 1; }
+            w.j = 0;
+            return true;
+          }
+          const bool more = (w.j + 1 < p.n_kt);
+          if (!mbar_try_wait(&v_full[w.vs], w.vph)) return false;
+          if (more && !mbar_try_wait(&k_full[w.ks], w.kph)) return false;
+          if (mine) {
+            if (!mbar_try_wait(&p_full[t], w.pph)) return false;
+            if (w.j == 0 && !mbar_try_wait(&o_empty[t], w.oeph ^ 1)) return false;
+            w.pph ^= 1;
+            if (w.j == 0) w.oeph ^= 1;
+            tc_fence_after();
+            att_trace<FLAGS>(p, 16 + t, w.gstep, 0);
+            issue_pv_s_q(t, w.vs, w.j > 0, more, w.ks, w.qbuf);
+            att_trace<FLAGS>(p, 16 + t, w.gstep, 1);
+            ++w.gstep;
+          }
+          commit(&v_empty[w.vs]);
+          if (++w.vs == KV_STAGES) { w.vs = 0; w.vph ^= 1; }
+          if (more) {
+            commit(&k_empty[w.ks]);
+            if (w.j + 2 == p.n_kt) commit(&q_empty[w.qbuf]);
+            if (++w.ks == KV_STAGES) { w.ks = 0; w.kph ^= 1; }
+            ++w.j;
+          } else {
+            if (mine) commit(&o_full[t]);
+            w.qph ^= 1u << w.qbuf;
+            w.qbuf ^= 1;
+            next_item(w);
+          }
+          return true;
+        };
+        Walk w0(p.n_items), w1(p.n_items);
+        Walk* ws[2] = {&w0, &w1};
+        for (int i = 0; i < 2; ++i) {
+          Walk& w = *ws[i];
+          w.t = t_lo + i; w.qbuf = 0; w.ks = 0; w.vs = 0;
+          w.qph = 0; w.kph = 0; w.vph = 0; w.pph = 0; w.oeph = 0; w.done = false;
+          next_item(w);
+        }
+        // one-time stagger of the four chains (t = 0,2,1,3 start a quarter step apart); the walkers keep
+        // whatever phase offset the chains have, they do not re-align them
+        if (p.stagger > 0) {
+          const long long t_begin = clock64();
+          const int mult0 = (t_lo == 0) ? 0 : 1, mult1 = (t_lo == 0) ? 2 : 3;
+          bool started0 = false, started1 = false;
+          while (!(started0 && started1)) {
+            const long long dt = clock64() - t_begin;
+            if (!started0 && (w0.done || dt >= (long long)mult0 * p.stagger)) started0 = w0.done || advance(w0);
+            if (!started1 && (w1.done || dt >= (long long)mult1 * p.stagger)) started1 = w1.done || advance(w1);
+            if (started0 && !w0.done) advance(w0);
+            if (dt > 4000000000LL) __trap();
+          }
+        }
+        long long last = clock64();
+        while (!(w0.done && w1.done)) {
+          bool prog = false;
+          if (!w0.done) prog |= advance(w0);
+          if (!w1.done) prog |= advance(w1);
+          if (prog) last = clock64();
+          else if (clock64() - last > 4000000000LL) {
+            printf("vf_attention: MMA walker stalled (block %d warp %d)\n", blockIdx.x, warp);
+            __trap();
+          }
+        }
+      } else {
       int item;
       for (ItemIter it(p.n_items); it.next(item);) {
         int b, h, qb;
@@ -311,6 +446,7 @@ attention_kernel(const AttnParams p, const __grid_constant__ CUtensorMap tmQ,
         qph ^= 1u << qbuf;
         qbuf ^= 1;
       }
+      }
     }
   } else {
     // ------------------------------------------------------------------ softmax warpgroups
@@ -321,95 +457,129 @@ attention_kernel(const AttnParams p, const __grid_constant__ CUtensorMap tmQ,
     const uint32_t s_addr = tmem_base + lane_sel + t * 64;
     const uint32_t o_addr = tmem_base + lane_sel + 256 + t * 64;
     const int r_local = quarter * 32 + lane;
-    uint32_t sph = 0, oph = 0, tph = 0;
+    uint32_t sph = 0, oph = 0;
+    int gstep = 0;   // key steps done by this warp (trace index)
 
     int item;
     for (ItemIter it(p.n_items); it.next(item);) {
       int b, h, qb;
       decode_item(p, item, b, h, qb);
       if (qb * (128 * NQ) + t * 128 >= p.S) continue;  // whole tile out of range (uniform per warp)
-      int nt_item = (p.S - qb * (128 * NQ) + 127) / 128;   // query tiles of this item (token ring size)
-      nt_item = nt_item > NQ ? NQ : nt_item;
       const int q_in_sample = qb * (128 * NQ) + t * 128 + r_local;
 
       float m = -INFINITY;   // running (possibly stale) row max, raw score units
       float l = 0.f;         // running row sum
       for (int j = 0; j < p.n_kt; ++j) {
+        att_trace<FLAGS>(p, warp, gstep, 0);
         att_wait(&s_full[t], sph); sph ^= 1;
         tc_fence_after();
+        att_trace<FLAGS>(p, warp, gstep, 1);
         // All MMAs issued before S_t(j) — in particular PV_t(j-1) — have retired: O_t is stable
         // until this warpgroup arrives on p_full[t].
         float s[KT];
         tmem_ld_x32(s_addr, reinterpret_cast<uint32_t*>(s));
         tmem_ld_x32(s_addr + 32, reinterpret_cast<uint32_t*>(s) + 32);
         tmem_ld_wait();
+        att_trace<FLAGS>(p, warp, gstep, 2);
         const int valid = p.S - j * KT;  // keys [0, valid) of this tile exist
         if (valid < KT) {
 #pragma unroll
           for (int c = 0; c < KT; ++c)
             if (c >= valid) s[c] = -INFINITY;
         }
-        float mx0 = fmaxf(s[0], s[1]), mx1 = fmaxf(s[2], s[3]);
+        auto row_max = [&]() {
+          float mx0 = fmaxf(s[0], s[1]), mx1 = fmaxf(s[2], s[3]);
 #pragma unroll
-        for (int c = 4; c < KT; c += 2) {
-          mx0 = fmaxf(mx0, s[c]);
-          mx1 = fmaxf(mx1, s[c + 1]);
-        }
-        const float mx = fmaxf(mx0, mx1);
-
-        if (j == 0) {
-          m = mx;
-        } else {
-          const bool grow = (mx - m) * p.scale_log2 > 8.0f;  // lazy rescale threshold: 2^8 headroom
-          if (__any_sync(0xffffffffu, grow)) {
+          for (int c = 4; c < KT; c += 2) {
+            mx0 = fmaxf(mx0, s[c]);
+            mx1 = fmaxf(mx1, s[c + 1]);
+          }
+          return fmaxf(mx0, mx1);
+        };
+        auto rescale_o = [&](float f) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint32_t o[16];
+            tmem_ld_x16(o_addr + c * 16, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 16; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * f);
+            tmem_st_x16(o_addr + c * 16, o);
+          }
+        };
+        if constexpr (FLAGS & ATT_LEAN) {
+          // P_t = exp2(s*c - m*c) as bf16 pairs over the first 32 columns of S_t; returns the row sum
+          auto exp_store = [&](float mb) {
+            const uint64_t sc2 = pack2(p.scale_log2, p.scale_log2), nb2 = pack2(-mb, -mb);
+            uint64_t acc0 = pack2(0.f, 0.f), acc1 = acc0;
+#pragma unroll
+            for (int c = 0; c < KT / 32; ++c) {
+              uint32_t pk[16];
+#pragma unroll
+              for (int e = 0; e < 16; ++e) {
+                float x0, x1;
+                unpack2(ffma2(pack2(s[c * 32 + 2 * e], s[c * 32 + 2 * e + 1]), sc2, nb2), x0, x1);
+                const float p0 = fast_exp2(x0), p1 = fast_exp2(x1);
+                if (e & 1) acc1 = fadd2(acc1, pack2(p0, p1));
+                else acc0 = fadd2(acc0, pack2(p0, p1));
+                pk[e] = pack_bf16(p0, p1);
+              }
+              tmem_st_x16(s_addr + c * 16, pk);
+            }
+            float a0, a1;
+            unpack2(fadd2(acc0, acc1), a0, a1);
+            return a0 + a1;
+          };
+          if (j == 0) m = row_max();
+          att_trace<FLAGS>(p, warp, gstep, 3);
+          float ssum = exp_store(m * p.scale_log2);
+          // runaway exponent (sum beyond 2^60, inf or NaN) in any row of the warp: redo the step with a fresh max
+          if (j > 0 && __any_sync(0xffffffffu, !(ssum <= 0x1p60f))) {
+            const float mx = row_max();
+            const bool grow = mx > m;
             const float f = grow ? fast_exp2((m - mx) * p.scale_log2) : 1.0f;
             if (grow) { m = mx; l *= f; }
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              uint32_t o[16];
-              tmem_ld_x16(o_addr + c * 16, o);
-              tmem_ld_wait();
-#pragma unroll
-              for (int e = 0; e < 16; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * f);
-              tmem_st_x16(o_addr + c * 16, o);
+            rescale_o(f);
+            ssum = exp_store(m * p.scale_log2);
+          }
+          l += ssum;
+        } else {
+          const float mx = row_max();
+          if (j == 0) {
+            m = mx;
+          } else {
+            const bool grow = (mx - m) * p.scale_log2 > 8.0f;  // lazy rescale threshold: 2^8 headroom
+            if (__any_sync(0xffffffffu, grow)) {
+              const float f = grow ? fast_exp2((m - mx) * p.scale_log2) : 1.0f;
+              if (grow) { m = mx; l *= f; }
+              rescale_o(f);
             }
           }
-        }
-        const float mb = m * p.scale_log2;
-        float sum0 = 0.f, sum1 = 0.f;
-        if constexpr (FLAGS & ATT_TOKEN) {   // my turn on this sub-partition's MUFU
-          att_wait(&tok[quarter * NQ + t], tph); tph ^= 1;
-        }
+          const float mb = m * p.scale_log2;
+          float sum0 = 0.f, sum1 = 0.f;
+          att_trace<FLAGS>(p, warp, gstep, 3);
 #pragma unroll
-        for (int c = 0; c < KT / 16; ++c) {
-          uint32_t pk[8];
-          if (!(FLAGS & ATT_TAILSKIP) || c * 16 < valid) {   // warp-uniform
+          for (int c = 0; c < KT / 32; ++c) {
+            uint32_t pk[16];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const float p0 = fast_exp2(fmaf(s[c * 16 + 2 * e], p.scale_log2, -mb));
-              const float p1 = fast_exp2(fmaf(s[c * 16 + 2 * e + 1], p.scale_log2, -mb));
+            for (int e = 0; e < 16; ++e) {
+              const float p0 = fast_exp2(fmaf(s[c * 32 + 2 * e], p.scale_log2, -mb));
+              const float p1 = fast_exp2(fmaf(s[c * 32 + 2 * e + 1], p.scale_log2, -mb));
               sum0 += p0;
               sum1 += p1;
               pk[e] = pack_bf16(p0, p1);
             }
-          } else {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) pk[e] = 0u;
+            tmem_st_x16(s_addr + c * 16, pk);   // P_t (bf16 pairs) over the first 32 columns of S_t
           }
-          tmem_st_x8(s_addr + c * 8, pk);   // P_t (bf16 pairs) over the first 32 columns of S_t
-          if constexpr (FLAGS & ATT_TOKEN) {
-            // hand the MUFU to the next chain once three quarters of this step's exponentials are
-            // issued (the rest overlaps the successor's first instructions)
-            if (c == KT / 16 - 2) {
-              if (lane == 0) mbar_arrive(&tok[quarter * NQ + (t + 1 == nt_item ? 0 : t + 1)]);
-            }
-          }
+          l += sum0 + sum1;
         }
-        l += sum0 + sum1;
+        att_trace<FLAGS>(p, warp, gstep, 4);
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[t]);
+        att_trace<FLAGS>(p, warp, gstep, 5);
+        ++gstep;
       }
 
       // ---- item epilogue: O_t / l -> global
@@ -454,6 +624,16 @@ attention_kernel(const AttnParams p, const __grid_constant__ CUtensorMap tmQ,
 
 using namespace vf;
 
+static unsigned long long* g_trace_buf = nullptr;
+static int g_trace_first = 0, g_trace_n = 0;
+
+extern "C" int vf_attention_set_trace(void* buf, int32_t first_step, int32_t n_steps) {
+  g_trace_buf = reinterpret_cast<unsigned long long*>(buf);
+  g_trace_first = first_step;
+  g_trace_n = buf ? n_steps : 0;
+  return VF_OK;
+}
+
 extern "C" int vf_attention_fwd(const void* qkv, void* out, int32_t B, int32_t S, int32_t H,
                                 float scale, void* stream) {
   VF_REQUIRE(qkv && out, VF_ERR_ARG, "vf_attention_fwd: null pointer");
@@ -480,15 +660,22 @@ extern "C" int vf_attention_fwd(const void* qkv, void* out, int32_t B, int32_t S
   e = encode_tmap(&tmKV, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, qkv, dims, strides, boxkv, CU_TENSOR_MAP_SWIZZLE_128B);
   if (e) return e;
 
-  // development switch: VF_ATTN_FLAGS selects a measured-slower variant for A/B runs
-  static int flags = -1;
+  // development switches: VF_ATTN_FLAGS selects the kernel variant, VF_ATTN_STAGGER the start offset (cycles)
+  static int flags = -1, stagger = 0;
   if (flags < 0) {
     const char* e_ = getenv("VF_ATTN_FLAGS");
-    flags = e_ ? atoi(e_) & 3 : 0;
+    const char* s_ = getenv("VF_ATTN_STAGGER");
+    stagger = s_ ? atoi(s_) : 0;
+    flags = e_ ? atoi(e_) & 7 : (ATT_ANYORDER | ATT_LEAN);
   }
+  p.stagger = stagger;
+  p.trace = g_trace_buf;
+  p.trace_first = g_trace_first;
+  p.trace_n = g_trace_n;
   using kern_t = void (*)(const AttnParams, const CUtensorMap, const CUtensorMap);
-  static const kern_t kerns[4] = {attention_kernel<0>, attention_kernel<1>, attention_kernel<2>, attention_kernel<3>};
-  static bool configured[4] = {false, false, false, false};
+  static const kern_t kerns[8] = {attention_kernel<0>, attention_kernel<1>, attention_kernel<2>, attention_kernel<3>,
+                                  attention_kernel<4>, attention_kernel<5>, attention_kernel<6>, attention_kernel<7>};
+  static bool configured[8] = {false, false, false, false, false, false, false, false};
   if (!configured[flags]) {
     VF_CUDA(cudaFuncSetAttribute(kerns[flags], cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem::TOTAL));
     configured[flags] = true;
