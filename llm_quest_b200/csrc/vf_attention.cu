@@ -29,7 +29,12 @@
 //   The MMA warp issues S_t(j+1) right behind PV_t(j); tcgen05.mma instructions of one thread retire
 //   in order, which is what makes the S/P aliasing and the in-place O rescale race-free.
 //
-//   Tried and measured slower on B200 (round 1): P in shared memory with S_t(j+1)
+//   Tried and measured slower on B200 (round 1): THREE chains with P in its own TMEM columns so
+//   that S_t(j+1) is computed while S_t(j) is exponentiated (one issuer warp per tile and product, exponentials
+//   kept in registers until PV_t(j-1) retires): 2.96 ms vs 2.23 ms at S=6272 — a chain's step is bound by the
+//   softmax warp's own ~2500-cycle serial path and by the issue cost of the small MMAs (~60 cycles per
+//   tcgen05.mma, ~100-200 per barrier operation), not by the QK^T round trip, so four chains beat three.
+//   Also: P in shared memory with S_t(j+1)
 //   issued as soon as S_t(j) is in registers (no MMA round trip on the softmax chain: 3.57 ms vs 3.28 ms
 //   per 12 layers), the same plus a per-sub-partition token that serialises the exp phases (3.71 ms),
 //   and a one-time stagger of the four chains (no effect).
@@ -81,6 +86,7 @@ struct AttnSmem {
 };
 
 __device__ __forceinline__ void att_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;   // fast path: no watchdog bookkeeping
   long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > 4000000000LL) {
@@ -620,6 +626,7 @@ attention_kernel(const AttnParams p, const __grid_constant__ CUtensorMap tmQ,
   }
 }
 
+
 }  // namespace vf
 
 using namespace vf;
@@ -660,7 +667,7 @@ extern "C" int vf_attention_fwd(const void* qkv, void* out, int32_t B, int32_t S
   e = encode_tmap(&tmKV, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, qkv, dims, strides, boxkv, CU_TENSOR_MAP_SWIZZLE_128B);
   if (e) return e;
 
-  // development switches: VF_ATTN_FLAGS selects the kernel variant, VF_ATTN_STAGGER the start offset (cycles)
+  // development switches: VF_ATTN_FLAGS = variant bits, VF_ATTN_STAGGER = one-time start offset in cycles
   static int flags = -1, stagger = 0;
   if (flags < 0) {
     const char* e_ = getenv("VF_ATTN_FLAGS");
@@ -672,6 +679,8 @@ extern "C" int vf_attention_fwd(const void* qkv, void* out, int32_t B, int32_t S
   p.trace = g_trace_buf;
   p.trace_first = g_trace_first;
   p.trace_n = g_trace_n;
+  const int sms = device_sm_count();
+  VF_REQUIRE(sms > 0, VF_ERR_NO_DEVICE, "no CUDA device");
   using kern_t = void (*)(const AttnParams, const CUtensorMap, const CUtensorMap);
   static const kern_t kerns[8] = {attention_kernel<0>, attention_kernel<1>, attention_kernel<2>, attention_kernel<3>,
                                   attention_kernel<4>, attention_kernel<5>, attention_kernel<6>, attention_kernel<7>};
@@ -680,8 +689,6 @@ extern "C" int vf_attention_fwd(const void* qkv, void* out, int32_t B, int32_t S
     VF_CUDA(cudaFuncSetAttribute(kerns[flags], cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem::TOTAL));
     configured[flags] = true;
   }
-  const int sms = device_sm_count();
-  VF_REQUIRE(sms > 0, VF_ERR_NO_DEVICE, "no CUDA device");
   const int grid = p.n_items < sms ? p.n_items : sms;
   kerns[flags]<<<grid, ATT_THREADS, AttnSmem::TOTAL, static_cast<cudaStream_t>(stream)>>>(p, tmQ, tmKV);
   count_launch();

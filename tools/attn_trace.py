@@ -39,9 +39,16 @@ for w in range(16):
         prev = r[0]
         print(f"t{tile}.q{q} step {first + i:4d}: start {r[0] - t0:8d}  waitS {r[1] - r[0]:5d}  ldtm {r[2] - r[1]:4d}  max {r[3] - r[2]:4d}  "
               f"exp {r[4] - r[3]:5d}  st+arr {r[5] - r[4]:4d} | period {per:5d}")
-print("# MMA walkers: tile: step: issue time(rel), issue duration")
+print("# MMA issuers: tile: step: S issue at(rel)/dur, PV issue at(rel)")
 for tile in range(4):
-    for i in range(min(n, 12)):
+    for i in range(min(n, 6)):
         r = [int(v) for v in t[16 + tile, i]]
+        if r[0] or r[2]:
+            print(f"mma t{tile} step {first + i:4d}: S at {r[0] - t0 if r[0] else -1:8d} dur {r[1] - r[0]:4d}   PV at {r[2] - t0 if r[2] else -1:8d}"
+                  f"   wait_sfree begin {r[4] - t0 if r[4] else -1:8d}  end {r[5] - t0 if r[5] else -1:8d}")
+print("# absolute stamps of tile chains (quarter 0): step: wait_begin S_ready ld_done exp_begin exp_end arrived")
+for tile in range(4):
+    for i in range(min(n, 4)):
+        r = [int(v) for v in t[tile * 4, i]]
         if r[0]:
-            print(f"mma t{tile} step {first + i:4d}: at {r[0] - t0:8d} dur {r[1] - r[0]:4d}")
+            print(f"abs t{tile} step {first + i:4d}: " + " ".join(f"{v - t0:7d}" for v in r[:6]))
