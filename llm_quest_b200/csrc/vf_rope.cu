@@ -84,45 +84,82 @@ rope_apply_kernel(const T* __restrict__ x, T* __restrict__ out, long long n_rows
   Ld4<T>::st(orow + i + half, o2);
 }
 
-// One warp per (b, h, s) row; lane l owns elements [l*EPL, (l+1)*EPL), EPL = hd/32 (4 or 8).
+// EPL consecutive elements of one lane kept in their storage format (so that eight rows in flight cost 32
+// registers at bf16 / head_dim 256), moved with the widest access the size allows.
+template <typename T, int EPL>
+struct LaneRaw {
+  static constexpr int NU = EPL * sizeof(T) / 8;   // 8-byte units: 1, 2 or 4
+  uint2 u[NU];
+  __device__ __forceinline__ void load(const T* p) {
+    if constexpr (NU == 1) {
+      u[0] = *reinterpret_cast<const uint2*>(p);
+    } else {
+#pragma unroll
+      for (int q = 0; q < NU / 2; ++q) {
+        const uint4 t = reinterpret_cast<const uint4*>(p)[q];
+        u[2 * q] = make_uint2(t.x, t.y);
+        u[2 * q + 1] = make_uint2(t.z, t.w);
+      }
+    }
+  }
+  __device__ __forceinline__ void store(T* p) const {
+    if constexpr (NU == 1) {
+      *reinterpret_cast<uint2*>(p) = u[0];
+    } else {
+#pragma unroll
+      for (int q = 0; q < NU / 2; ++q)
+        reinterpret_cast<uint4*>(p)[q] = make_uint4(u[2 * q].x, u[2 * q].y, u[2 * q + 1].x, u[2 * q + 1].y);
+    }
+  }
+  __device__ __forceinline__ void unpack(float (&v)[EPL]) const {
+    if constexpr (sizeof(T) == 2) {
+#pragma unroll
+      for (int q = 0; q < NU; ++q) {
+        v[4 * q] = bf16_lo(u[q].x); v[4 * q + 1] = bf16_hi(u[q].x);
+        v[4 * q + 2] = bf16_lo(u[q].y); v[4 * q + 3] = bf16_hi(u[q].y);
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < NU; ++q) { v[2 * q] = __uint_as_float(u[q].x); v[2 * q + 1] = __uint_as_float(u[q].y); }
+    }
+  }
+  __device__ __forceinline__ void pack(const float (&v)[EPL]) {
+    if constexpr (sizeof(T) == 2) {
+#pragma unroll
+      for (int q = 0; q < NU; ++q) u[q] = make_uint2(pack_bf16(v[4 * q], v[4 * q + 1]), pack_bf16(v[4 * q + 2], v[4 * q + 3]));
+    } else {
+#pragma unroll
+      for (int q = 0; q < NU; ++q) u[q] = make_uint2(__float_as_uint(v[2 * q]), __float_as_uint(v[2 * q + 1]));
+    }
+  }
+};
+
+// One warp per TOKEN (b, s): the position ids and the gathered cos/sin coefficients depend on the token
+// only, so they are fetched once and reused for every head; the heads' rows (512 B each at head_dim 256
+// bf16) are loaded eight at a time before any arithmetic, which is what keeps enough bytes in flight
+// (one row per warp with the id -> table -> x dependency chain reached only 22 % of the copy bandwidth).
+// Lane l owns elements [l*EPL, (l+1)*EPL) of a row, EPL = hd/32 (4 or 8).
 template <typename T, int EPL>
 __global__ void __launch_bounds__(256)
-mrope_apply_kernel(const T* __restrict__ x, T* __restrict__ out, long long n_rows, int B, int H, int S,
+mrope_apply_kernel(const T* __restrict__ x, T* __restrict__ out, int B, int H, int S,
                    const float* __restrict__ cos, const float* __restrict__ sin, int rot,
                    const long long* __restrict__ position_ids, int sec_h, int sec_w,
                    const float* __restrict__ norm_w, float norm_eps) {
   constexpr int HD = EPL * 32;
+  constexpr int HC = sizeof(T) == 2 ? 8 : 4;   // heads (rows) in flight per warp
   const int lane = threadIdx.x & 31;
-  const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= n_rows) return;
-  const int s = static_cast<int>(row % S);
-  const long long b = row / (static_cast<long long>(S) * H);
-
-  float v[EPL];
-  const T* xr = x + row * HD + lane * EPL;
-#pragma unroll
-  for (int q = 0; q < EPL / 4; ++q) Ld4<T>::ld(xr + q * 4, *reinterpret_cast<float(*)[4]>(&v[q * 4]));
-
-  if (norm_w) {
-    float ss = 0.f;
-#pragma unroll
-    for (int e = 0; e < EPL; ++e) ss = fmaf(v[e], v[e], ss);
-    const float rms = rsqrtf(warp_sum(ss) * (1.0f / HD) + norm_eps);
-#pragma unroll
-    for (int e = 0; e < EPL; ++e) {
-      float y = v[e] * rms * norm_w[lane * EPL + e];
-      if (sizeof(T) == 2) y = __bfloat162float(__float2bfloat16_rn(y));  // the norm returns x.dtype
-      v[e] = y;
-    }
-  }
+  const long long tok = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (tok >= static_cast<long long>(B) * S) return;
+  const int s = static_cast<int>(tok % S);
+  const long long b = tok / S;
 
   const int half = rot >> 1;
   const int lanes_half = half / EPL;  // lanes holding the first half of the rotated block
-  // partner element (j <-> j+half) lives lanes_half lanes away
-  float partner[EPL];
-#pragma unroll
-  for (int e = 0; e < EPL; ++e) partner[e] = __shfl_xor_sync(0xffffffffu, v[e], lanes_half);
-  if (lane < 2 * lanes_half) {
+  const bool rotates = lane < 2 * lanes_half;
+  // out = c*v + sg*partner with sg = -sin for the first half and +sin for the second: the same two rounded
+  // products and one rounded sum as the reference's cos*x + sin*rotate_half(x)
+  float c[EPL], sg[EPL], w[EPL];
+  if (rotates) {
     const bool first = lane < lanes_half;
     const long long pt = position_ids[(0LL * B + b) * S + s];
     const long long ph = position_ids[(1LL * B + b) * S + s];
@@ -134,19 +171,55 @@ mrope_apply_kernel(const T* __restrict__ x, T* __restrict__ out, long long n_row
       long long pos = pt;
       if (r3 == 1 && j < 3 * sec_h) pos = ph;
       if (r3 == 2 && j < 3 * sec_w) pos = pw;
-      const float c = cos[pos * rot + j];
-      const float sn = sin[pos * rot + j];
-      if (sizeof(T) == 4) {
-        v[e] = first ? __fsub_rn(__fmul_rn(c, v[e]), __fmul_rn(sn, partner[e]))
-                     : __fadd_rn(__fmul_rn(c, v[e]), __fmul_rn(sn, partner[e]));
-      } else {
-        v[e] = first ? (c * v[e] - sn * partner[e]) : (c * v[e] + sn * partner[e]);
-      }
+      c[e] = __ldg(cos + pos * rot + j);
+      const float sn = __ldg(sin + pos * rot + j);
+      sg[e] = first ? -sn : sn;
     }
   }
-  T* orow = out + row * HD + lane * EPL;
+  if (norm_w) {
 #pragma unroll
-  for (int q = 0; q < EPL / 4; ++q) Ld4<T>::st(orow + q * 4, *reinterpret_cast<float(*)[4]>(&v[q * 4]));
+    for (int q = 0; q < EPL / 4; ++q) Ld4<float>::ld(norm_w + lane * EPL + q * 4, *reinterpret_cast<float(*)[4]>(&w[q * 4]));
+  }
+
+  const long long head_stride = static_cast<long long>(S) * HD;
+  const long long base = (b * H * S + s) * HD + lane * EPL;
+  for (int h0 = 0; h0 < H; h0 += HC) {
+    LaneRaw<T, EPL> raw[HC];
+#pragma unroll
+    for (int i = 0; i < HC; ++i)
+      if (h0 + i < H) raw[i].load(x + base + (h0 + i) * head_stride);
+#pragma unroll
+    for (int i = 0; i < HC; ++i) {
+      if (h0 + i >= H) break;
+      float v[EPL];
+      raw[i].unpack(v);
+      if (norm_w) {
+        float ss = 0.f;
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) ss = fmaf(v[e], v[e], ss);
+        const float rms = rsqrtf(warp_sum(ss) * (1.0f / HD) + norm_eps);
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) {
+          float y = v[e] * rms * w[e];
+          if (sizeof(T) == 2) y = __bfloat162float(__float2bfloat16_rn(y));  // the norm returns x.dtype
+          v[e] = y;
+        }
+      }
+      // partner element (j <-> j+half) lives lanes_half lanes away
+      float partner[EPL];
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) partner[e] = __shfl_xor_sync(0xffffffffu, v[e], lanes_half);
+      if (rotates) {
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) {
+          if (sizeof(T) == 4) v[e] = __fadd_rn(__fmul_rn(c[e], v[e]), __fmul_rn(sg[e], partner[e]));
+          else v[e] = c[e] * v[e] + sg[e] * partner[e];
+        }
+      }
+      raw[i].pack(v);
+      raw[i].store(out + base + (h0 + i) * head_stride);
+    }
+  }
 }
 
 }  // namespace vf
@@ -198,12 +271,15 @@ extern "C" int vf_mrope_apply(const void* x, void* out, int32_t dtype, int32_t B
   VF_REQUIRE(sec_t + sec_h + sec_w == rot / 2, VF_ERR_ARG,
              "vf_mrope_apply: mrope_section must sum to rot/2 (%d+%d+%d != %d)", sec_t, sec_h, sec_w, rot / 2);
   (void)table_rows;
-  const long long rows = (long long)B * H * S;
-  const unsigned grid = (unsigned)((rows + 7) / 8);
+  VF_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
+                 (reinterpret_cast<uintptr_t>(norm_weight) & 15) == 0,
+             VF_ERR_ALIGN, "vf_mrope_apply: pointers must be 16-byte aligned");
+  const long long tokens = (long long)B * S;
+  const unsigned grid = (unsigned)((tokens + 7) / 8);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const long long* pid = reinterpret_cast<const long long*>(position_ids);
 #define VF_MROPE(T, EPL)                                                                           \
-  mrope_apply_kernel<T, EPL><<<grid, 256, 0, s>>>((const T*)x, (T*)out, rows, B, H, S, cos, sin, rot, pid, \
+  mrope_apply_kernel<T, EPL><<<grid, 256, 0, s>>>((const T*)x, (T*)out, B, H, S, cos, sin, rot, pid, \
                                                   sec_h, sec_w, norm_weight, norm_eps)
   if (dtype == 0 && hd == 256) VF_MROPE(float, 8);
   else if (dtype == 0 && hd == 128) VF_MROPE(float, 4);

@@ -56,6 +56,11 @@ class Qwen3_5VLM(nn.Module):
             except ImportError:
                 language_model = EmbeddingOnlyLM(self.cfg)
         self.language_model = language_model
+        # vision-feature cache: the reference's generate loop re-encodes the same image for
+        # every new token (qwen3_5_generate_multimodal.py:107-123); with the cache on, the tower runs once per
+        # pixel tensor and later calls only redo the (cheap) gather/scatter + position ids
+        self._vision_cache_on = False
+        self._vision_cache = None   # (signature, merged rows bf16 [n_vis, D])
 
     # -- reference API ----------------------------------------------------------------------------
     def get_feeds_3d_shape(self, image_pixels):
@@ -79,6 +84,38 @@ class Qwen3_5VLM(nn.Module):
             mask = torch.zeros((b, seq_len), dtype=torch.uint8, device=input_ids.device)
             return _lib.mrope_position_ids(input_ids, mask, self.image_token_id, feeds, self.merge_size)
         return _lib.mrope_position_ids(input_ids, image_mask, self.image_token_id, feeds_3d_shape, self.merge_size)
+
+    # -- vision-feature cache ------------------------------------------------------------------------
+    def enable_vision_cache(self, on: bool = True):
+        """Keep the merged vision embeddings of the last ``image_pixels`` tensor and reuse them while the
+        same tensor (storage, shape, version) is passed again and the tower's weights are unchanged.
+        Off by default: the reference recomputes every call."""
+        self._vision_cache_on = bool(on)
+        if not on:
+            self._vision_cache = None
+        return self
+
+    def clear_vision_cache(self):
+        self._vision_cache = None
+
+    def _vision_signature(self, image_pixels):
+        ver = lambda t: 0 if t.is_inference() else t._version
+        sig = [(image_pixels.data_ptr(), tuple(image_pixels.shape), image_pixels.dtype, ver(image_pixels))]
+        for prm in self.vision_model.parameters():
+            sig.append((prm.data_ptr(), ver(prm)))
+        return tuple(sig)
+
+    def _cached_vision_rows(self, image_pixels, n_vis, D):
+        sig = self._vision_signature(image_pixels)
+        hit = self._vision_cache
+        if hit is not None and hit[0] == sig:
+            return hit[1]
+        rows = torch.empty((n_vis, D), dtype=torch.bfloat16, device=image_pixels.device)
+        vm = self.vision_model
+        x2d, _, _ = vm.encode_hidden(image_pixels)
+        vm.merge_adapter.merge_project(x2d, out=rows)
+        self._vision_cache = (sig, rows)
+        return rows
 
     # -- the fused path ---------------------------------------------------------------------------
     def encode_and_fuse(self, input_ids, image_pixels=None, feeds_3d_shape=None, check=True):
@@ -111,9 +148,14 @@ class Qwen3_5VLM(nn.Module):
                     raise RuntimeError(
                         f"masked_scatter: {n} image placeholders in input_ids but the vision tower yields only {n_vis} rows"
                     )
-            # text rows: gathered from the table; placeholder rows are written by the merger GEMM epilogue
-            _lib.embed_gather_scatter(input_ids, table.detach(), None, row_map, inputs_embs, skip_vision=True, n_vis=n_vis)
-            vm(image_pixels, out=inputs_embs.view(b * seq, D), dst_rows=dst)
+            if self._vision_cache_on:
+                # one kernel moves text rows from the table and vision rows from the cached embeddings
+                rows = self._cached_vision_rows(image_pixels, n_vis, D)
+                _lib.embed_gather_scatter(input_ids, table.detach(), rows, row_map, inputs_embs)
+            else:
+                # text rows: gathered from the table; placeholder rows are written by the merger GEMM epilogue
+                _lib.embed_gather_scatter(input_ids, table.detach(), None, row_map, inputs_embs, skip_vision=True, n_vis=n_vis)
+                vm(image_pixels, out=inputs_embs.view(b * seq, D), dst_rows=dst)
             image_mask = (row_map >= 0).view(b, seq)
             if feeds_3d_shape is None:
                 feeds_3d_shape = self.get_feeds_3d_shape(image_pixels)

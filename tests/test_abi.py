@@ -142,3 +142,46 @@ def test_shim_aliases_reference_module_paths():
                 sys.modules.pop(k, None)
             else:
                 sys.modules[k] = v
+
+
+def test_hf_vision_weight_remap_round_trip():
+    """HF names -> ours (reference qwen3_5_weight_loading.py:60-81); every tower parameter is
+    reachable from an HF-named dict, shapes are checked, non-vision keys are ignored."""
+    import torch
+
+    from llm_quest_b200.qwen.qwen3_5 import qwen3_5_weight_loading as WL
+    from llm_quest_b200.qwen.qwen3_5.qwen3_5_vision_model import Qwen3_5VisionModel
+
+    cfg = {"vision_emb_dim": 128, "vision_n_layers": 2, "vision_num_heads": 2, "vision_hidden_dim": 256,
+           "vision_rope_base": 10_000, "llm_d_in": 64, "img_width": 64, "img_height": 64, "patch_size": 16,
+           "in_channels": 3, "temporal_patch_size": 2, "spatial_merge_size": 2, "num_position_embeddings": 16}
+    torch.manual_seed(0)
+    src = Qwen3_5VisionModel(cfg)
+    inv = [(b, a) for a, b in WL.get_vision_remapping_rules()]
+
+    def to_hf(k):
+        if k.startswith("blocks."):
+            k = "model.visual." + k
+            for ours, hf in ((".att.qkv.", ".attn.qkv."), (".att.proj.", ".attn.proj."), (".ffn.lin1.", ".mlp.linear_fc1."),
+                             (".ffn.lin2.", ".mlp.linear_fc2.")):
+                k = k.replace(ours, hf)
+            return k
+        for ours, hf in inv:
+            if k.startswith(ours):
+                return hf + k[len(ours):]
+        raise AssertionError(k)
+
+    hf = {to_hf(k): v.clone() for k, v in src.state_dict().items()}
+    hf["model.language_model.layers.0.mlp.up_proj.weight"] = torch.zeros(3)
+    hf["mtp.fc.weight"] = torch.zeros(3)
+    assert all(k.startswith(("model.visual.", "model.language_model.", "mtp.")) for k in hf)
+    torch.manual_seed(1)
+    dst = Qwen3_5VisionModel(cfg)
+    missing, unexpected = WL.load_qwen3_5_vision_weights(dst, hf)
+    assert missing == [] and unexpected == []
+    for k, v in src.state_dict().items():
+        assert torch.equal(dst.state_dict()[k], v), k
+    bad = dict(hf)
+    bad["model.visual.merger.linear_fc2.weight"] = torch.zeros(2, 2)
+    with pytest.raises(ValueError, match="shape"):
+        WL.convert_vision_weights(bad, dst.state_dict())

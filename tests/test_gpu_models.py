@@ -209,3 +209,125 @@ def test_vlm_encode_and_fuse_vs_oracle():
     with pytest.raises(RuntimeError, match="masked_scatter"):
         vlm.encode_and_fuse(ids_bad.cuda(), pixels.cuda())
     assert FO.feeds_3d_shape(tuple(pixels.shape), px // 16, px // 16, 2).tolist() == vlm.get_feeds_3d_shape(pixels).tolist()
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE.json configs 3-5 at the shapes that stress the kernels (depth reduced so that the CPU oracle
+# finishes in seconds: every layer runs the same kernels) and size-independent properties at full size
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("px,T,layers,npos,what", [
+    (448, 16, 1, 2304, "cfg-4 video: 16 frames -> T'=8, S=6272 (49 query tiles, 98 key tiles)"),
+    (672, 2, 2, 7056, "cfg-5 sweep 672 px: S=1764, pos-embed capacity 7056"),
+    (1344, 2, 1, 7056, "cfg-5 sweep 1344 px: S=7056 = the whole pos-embed table"),
+    (224, 8, 2, 2304, "cfg-3 forward()-native clip: 8 frames 224 px, cross-frame attention, S=784"),
+])
+def test_qwen_tower_config_shapes_vs_oracle(px, T, layers, npos, what):
+    from llm_quest_b200.qwen.qwen3_5.qwen3_5_vision_model import Qwen3_5VisionModel
+
+    cfg = qwen_cfg(px, vision_n_layers=layers, num_position_embeddings=npos)
+    torch.manual_seed(123)
+    m = Qwen3_5VisionModel(cfg).eval()
+    sd = _random_qwen_sd(m)
+    m.load_state_dict(sd)
+    pixels = torch.randn(1, 3, T, px, px, generator=torch.Generator().manual_seed(1234)).to(torch.bfloat16).float()
+    with torch.inference_mode():
+        ref = VO.qwen_vision_forward(sd, cfg, pixels)
+        out = m.cuda()(pixels.cuda())
+    assert out.shape == (1, (T // 2) * (px // 32) ** 2, 1024)
+    check_close(out, ref, what)
+
+
+def test_full_batch_equals_single_samples_bit_exact():
+    """cfg-2 at FULL size (64 x 448^2, 12 layers): no op mixes samples, so a sample's output must not depend
+    on the batch it travels in — bit for bit (same tiles, same accumulation order), and a second run of the
+    same batch is identical (no atomics, no race)."""
+    from llm_quest_b200.qwen.qwen3_5.qwen3_5_vision_model import Qwen3_5VisionModel
+
+    torch.manual_seed(123)
+    m = Qwen3_5VisionModel(qwen_cfg(448)).eval().cuda()
+    x = torch.randn(64, 3, 2, 448, 448, generator=torch.Generator().manual_seed(1234)).to(torch.bfloat16).cuda()
+    with torch.inference_mode():
+        full = m(x)
+        again = m(x)
+        part = m(x[[5, 37, 63]].contiguous())
+    assert torch.isfinite(full).all()
+    assert torch.equal(full, again), "two runs of the same batch differ"
+    assert torch.equal(full[[5, 37, 63]], part), "a sample's embedding depends on its batch neighbours"
+
+
+def test_vlm_cfg3_full_size_placement_and_ids():
+    """cfg-3 at FULL size (32 samples x (4 images + 2048 text tokens), seq 2832): scatter placement, untouched
+    rows and MRoPE-I ids bit-exact against the numpy oracle; vision rows equal the tower's own output."""
+    from llm_quest_b200.qwen.qwen3_5.qwen3_5_vlm_model import Qwen3_5VLM
+
+    cfg = qwen_cfg(448, vision_n_layers=1, vocab_size=4096)
+    torch.manual_seed(123)
+    vlm = Qwen3_5VLM(cfg).eval().cuda()
+    g = torch.Generator().manual_seed(4321)
+    b, n_img, per = 32, 4, 196
+    chunks = [410, 410, 410, 410, 408]
+    rows = []
+    for _ in range(b):
+        parts = []
+        for i, c in enumerate(chunks):
+            parts.append(torch.randint(0, 1000, (c,), generator=g))
+            if i < n_img:
+                parts.append(torch.full((per,), IMG, dtype=torch.int64))
+        rows.append(torch.cat(parts))
+    ids = torch.stack(rows)
+    assert ids.shape == (b, 2832)
+    pixels = torch.randn(b * n_img, 3, 2, 448, 448, generator=g).to(torch.bfloat16)
+    feeds = torch.tensor([[1, 28, 28]] * n_img)
+    with torch.inference_mode():
+        embs, pid, mask = vlm.encode_and_fuse(ids.cuda(), pixels.cuda(), feeds)
+        vis = vlm.vision_model(pixels.cuda())
+    assert torch.equal(mask.cpu(), ids == IMG)
+    exp_pid = FO.mrope_position_ids(ids.numpy(), feeds.tolist(), None, IMG, 2)
+    assert torch.equal(pid.cpu(), torch.from_numpy(exp_pid)) and int(pid.max()) == 2103
+    got = embs.view(-1, 1024)
+    flat = ids.view(-1).cuda()
+    table = vlm.language_model.emb_dict.weight.detach()
+    assert torch.equal(got[flat != IMG].view(torch.uint16), table[flat[flat != IMG]].view(torch.uint16))
+    # vision rows land in flat (b, seq) order; the scatter epilogue rounds fp32 -> bf16 once
+    assert torch.equal(got[flat == IMG], vis.reshape(-1, 1024).to(torch.bfloat16))
+
+
+def test_vision_feature_cache_decode_loop():
+    """in a decode loop the image is encoded once; later steps only gather/scatter. The cached
+    path must give the same embeddings bit for bit and launch a handful of kernels instead of the tower."""
+    from llm_quest_b200 import _lib
+    from llm_quest_b200.qwen.qwen3_5.qwen3_5_vlm_model import Qwen3_5VLM
+
+    px = 64
+    cfg = qwen_cfg(px, vision_n_layers=2, vocab_size=3000, image_token_id=2999)
+    torch.manual_seed(123)
+    vlm = Qwen3_5VLM(cfg).eval().cuda()
+    tok, n_vis = 2999, (px // 32) ** 2
+    g = torch.Generator().manual_seed(7)
+    ids = torch.randint(0, 1000, (2, 20), generator=g)
+    ids[:, 3:3 + n_vis] = tok
+    pixels = torch.randn(2, 3, 2, px, px, generator=g).to(torch.bfloat16).cuda()
+    with torch.inference_mode():
+        ref_e, ref_p, _ = vlm.encode_and_fuse(ids.cuda(), pixels)
+        vlm.enable_vision_cache()
+        _lib.reset_launch_count()
+        e1, p1, _ = vlm.encode_and_fuse(ids.cuda(), pixels)
+        first = _lib.launch_count()
+        ids2 = torch.cat([ids, torch.randint(0, 1000, (2, 1), generator=g)], dim=1)   # one generated token later
+        _lib.reset_launch_count()
+        e2, p2, _ = vlm.encode_and_fuse(ids2.cuda(), pixels)
+        second = _lib.launch_count()
+    assert torch.equal(e1, ref_e) and torch.equal(p1, ref_p)
+    assert torch.equal(e2[:, :20], ref_e) and torch.equal(p2[:, :, :20], ref_p)
+    assert second <= 6 < first, (first, second)          # scan + gather/scatter + position ids vs the whole tower
+    # a changed image (new tensor version) or changed weights must miss
+    with torch.no_grad():
+        pixels2 = pixels.clone()
+        pixels2 += 1.0
+        _lib.reset_launch_count()
+        e3, _, _ = vlm.encode_and_fuse(ids.cuda(), pixels2)
+        assert _lib.launch_count() > 6 and not torch.equal(e3, ref_e)
+        vlm.vision_model.merge_adapter.lin2.bias.add_(1.0)
+        _lib.reset_launch_count()
+        vlm.encode_and_fuse(ids.cuda(), pixels2)
+        assert _lib.launch_count() > 6
