@@ -63,6 +63,15 @@ def measured_peaks():
     return {"bf16_tflops": 1400.0, "bf16_tflops_burst": 1590.0, "hbm_gbs": 6650.0, "source": "fallback"}
 
 
+def measured_traffic():
+    """DRAM bytes per launch of the dominant kernel family from the committed ncu --set full capture."""
+    files = sorted((ROOT / "profiles").glob("*_traffic.json"))
+    if not files:
+        return None, None
+    d = json.loads(files[-1].read_text())
+    return d.get("gemm_family_avg_dram_bytes_per_launch"), files[-1].name
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
 
@@ -277,7 +286,9 @@ def run_ours(args):
             "step_tflops": round(step_tflops, 1), "step_frac_of_peak": round(step_tflops / peaks["bf16_tflops"], 3),
             "roofline": {"bound": "tensor", "kernel": "vf::gemm_kernel<EPI,BN> (tcgen05, all epilogues; incl. patch-embed gather GEMM)",
                          "achieved": round(achieved, 1), "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                         "frac": round(achieved / peaks["bf16_tflops"], 3), "traffic": None, "peak_source": peaks["source"] + " (sustained cuBLAS bf16)",
+                         "frac": round(achieved / peaks["bf16_tflops"], 3), "traffic": measured_traffic()[0],
+                         "traffic_unit": "DRAM bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, avg over the family)",
+                         "traffic_source": measured_traffic()[1], "peak_source": peaks["source"] + " (sustained cuBLAS bf16)",
                          "launches_per_step": gemm_n // 2, "avg_launch_ms": round(gemm_ms / max(gemm_n, 1), 4),
                          "share_of_step": round(gemm_ms / all_ms, 3)},
             "kernels": breakdown,

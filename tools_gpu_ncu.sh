@@ -1,6 +1,7 @@
 #!/bin/bash
-# ncu evidence: full capture of the dominant kernels (one forward pass of cfg-2 after one warm-up pass)
+# ncu evidence for profiles/: launch list of the bench command + full captures of the dominant kernels
 mkdir -p gpurun_out
+rm -f gpurun_out/prof_*.ncu-rep
 cat > /tmp/one_step.py <<'PY'
 import sys, torch
 sys.path.insert(0, '.')
@@ -15,14 +16,14 @@ with torch.inference_mode():
         m(x)
 torch.cuda.synchronize()
 PY
-if true; then
-ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv python /tmp/one_step.py 2 > gpurun_out/ncu_list.log 2>&1
+# (1) launch list of the SAME command the bench line comes from (shares must agree with bench.py's CUDA-event shares)
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 --no-cpu > gpurun_out/ncu_list.log 2>&1
 echo "list exit=$?"
-fi
-ncu --set full --clock-control none --import-source on -k regex:gemm_kernel -s 54 -c 4 -o gpurun_out/prof_gemm -f python /tmp/one_step.py 2 > gpurun_out/ncu_gemm.log 2>&1
+# (2) full captures, second forward pass (layer 5): qkv, proj, lin1, lin2 GEMMs; attention; layernorm
+ncu --set full --clock-control none --import-source on -k regex:gemm_kernel -s 72 -c 4 -o gpurun_out/prof_gemm -f python /tmp/one_step.py 2 > gpurun_out/ncu_gemm.log 2>&1
 echo "gemm exit=$?"
-ls -la gpurun_out/*.ncu-rep
-ncu --set full --clock-control none --import-source on -k regex:attention_kernel -s 13 -c 1 -o gpurun_out/prof_attn -f python /tmp/one_step.py 2 > gpurun_out/ncu_attn.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:attention_kernel -s 17 -c 1 -o gpurun_out/prof_attn -f python /tmp/one_step.py 2 > gpurun_out/ncu_attn.log 2>&1
 echo "attn exit=$?"
-ncu --set full --clock-control none -k regex:layernorm_kernel -s 30 -c 1 -o gpurun_out/prof_ln -f python /tmp/one_step.py 2 > gpurun_out/ncu_ln.log 2>&1
+ncu --set full --clock-control none -k regex:layernorm_kernel -s 35 -c 1 -o gpurun_out/prof_ln -f python /tmp/one_step.py 2 > gpurun_out/ncu_ln.log 2>&1
 echo "ln exit=$?"
+ls -la gpurun_out/*.ncu-rep
