@@ -337,6 +337,24 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
         }
       }
 
+      // Residual epilogue: the residual values of a 32-column block are requested one block ahead of their use
+      // (block 0 before the accumulator is even complete), into the registers the previous block just freed.
+      [[maybe_unused]] float4 ex[8];
+      [[maybe_unused]] const bool fast_res = p.vec_ok && ((p.N & 3) == 0);
+      [[maybe_unused]] auto load_res = [&](int c) {
+        if constexpr (EPI == VF_EPI_BIAS_RES_F32 && !PATCH) {
+          const int cc = col0 + chalf * COLS_PER_WARP + c * 32 + cl * 4;
+          if (fast_res && cc < p.N) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const long long o = orow[i] < 0 ? 0 : orow[i];
+              ex[i] = *reinterpret_cast<const float4*>(p.res + o * p.ldr + cc);
+            }
+          }
+        }
+      };
+      load_res(0);
+
       wait_or_trap(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + chalf * COLS_PER_WARP;
@@ -428,11 +446,6 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
             if (p.bias) bv = __ldg(reinterpret_cast<const float4*>(p.bias + cc));
             // residual / pos-embed values of all 8 rows are fetched up front: they may alias `out`, so
             // the compiler cannot hoist them across the stores by itself
-            float4 ex[8];
-            if constexpr (EPI == VF_EPI_BIAS_RES_F32) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) ex[i] = *reinterpret_cast<const float4*>(rbase[i] + cc * 4);
-            }
             if constexpr (PATCH) {
 #pragma unroll
               for (int i = 0; i < 8; ++i)
@@ -466,6 +479,7 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
             };
             if (rows_all_valid) do_rows(std::false_type{});
             else do_rows(std::true_type{});
+            if (c + 1 < COLS_PER_WARP / 32) load_res(c + 1);
           } else {
             // generic path (unaligned rows or N % 4 != 0, e.g. a 10-class head): scalar, per-element guards
 #pragma unroll
