@@ -199,6 +199,16 @@ int vf_embed_gather_scatter(const int64_t* input_ids, const void* table, int64_t
 int vf_cast_f32_to_bf16(const float* x, void* out, int64_t n, void* stream);
 int vf_cast_bf16_to_f32(const void* x, float* out, int64_t n, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * uint8 image -> normalised pixel tensor for PatchEmbedding3D. Replaces, after the
+ * host-side resize, to_tensor + normalize + temporal duplication + permute of
+ *   llm_quest/qwen/qwen3_5/qwen3_5_generate_multimodal.py:40-46 (and dataset.py:336-351).
+ * img: uint8 [B, H, W, 3] (HWC, device); mean3 / std3: HOST float[3]; out: [B, 3, T, H, W] fp32 (out_dtype 0,
+ * bit-identical to torchvision) or bf16 (1); every temporal slot holds the same frame. W % 4 == 0.
+ * ------------------------------------------------------------------------------------------- */
+int vf_preprocess_u8(const uint8_t* img, int32_t B, int32_t H, int32_t W, int32_t T, const float* mean3,
+                     const float* std3, void* out, int32_t out_dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -29,7 +29,7 @@ EXPORTS = [
     "vf_version", "vf_last_error", "vf_launch_count", "vf_launch_count_reset", "vf_gemm_bf16",
     "vf_patch_embed", "vf_attention_fwd", "vf_attention_set_trace", "vf_layernorm", "vf_vit_cls_pos", "vf_rope_apply",
     "vf_mrope_apply", "vf_mrope_position_ids", "vf_fuse_scan", "vf_embed_gather_scatter",
-    "vf_cast_f32_to_bf16", "vf_cast_bf16_to_f32",
+    "vf_cast_f32_to_bf16", "vf_cast_bf16_to_f32", "vf_preprocess_u8",
 ]
 
 
@@ -89,6 +89,7 @@ def lib() -> C.CDLL:
         "vf_embed_gather_scatter": [vp, vp, i64, i32, vp, i32, i64, vp, vp, i64, i32, vp],
         "vf_cast_f32_to_bf16": [vp, vp, i64, vp],
         "vf_cast_bf16_to_f32": [vp, vp, i64, vp],
+        "vf_preprocess_u8": [vp, i32, i32, i32, i32, C.POINTER(C.c_float), C.POINTER(C.c_float), vp, i32, vp],
     }
     for name, args in sigs.items():
         fn = getattr(L, name)
@@ -370,4 +371,18 @@ def to_f32(x):
     out = torch.empty(xc.shape, dtype=torch.float32, device=x.device)
     with _timed("cast", bytes=6.0 * xc.numel()):
         check(lib().vf_cast_bf16_to_f32(xc.data_ptr(), out.data_ptr(), xc.numel(), _stream()), "vf_cast_bf16_to_f32")
+    return out
+
+
+def preprocess_u8(img_u8, mean, std, T=2, dtype=torch.bfloat16):
+    """uint8 [B, H, W, 3] (cuda) -> normalised [B, 3, T, H, W] (every temporal slot = the frame)."""
+    _require_cuda(img_u8)
+    assert img_u8.dtype == torch.uint8 and img_u8.dim() == 4 and img_u8.shape[-1] == 3 and img_u8.is_contiguous()
+    B, H, W, _ = img_u8.shape
+    out = torch.empty((B, 3, T, H, W), dtype=dtype, device=img_u8.device)
+    m3 = (C.c_float * 3)(*[float(v) for v in mean])
+    s3 = (C.c_float * 3)(*[float(v) for v in std])
+    with _timed("preprocess_u8", bytes=float(B * H * W * 3 * (1 + T * out.element_size()))):
+        check(lib().vf_preprocess_u8(img_u8.data_ptr(), B, H, W, T, m3, s3, out.data_ptr(), _DT[dtype], _stream()),
+              "vf_preprocess_u8")
     return out

@@ -253,6 +253,18 @@ def vit_adapter_forward(sd: dict, x: torch.Tensor):
     return y + sd["adapter.3.bias"] if "adapter.3.bias" in sd else y
 
 
+def preprocess_u8(images_u8: torch.Tensor, mean, std, temporal_patch_size: int = 2) -> torch.Tensor:
+    """uint8 [B, H, W, 3] -> fp32 [B, 3, T, H, W], the pre-processing that feeds PatchEmbedding3D
+    (qwen3_5_generate_multimodal.py:40-46 after the resize): torchvision to_tensor (HWC -> CHW, / 255),
+    normalize ((x - mean) / std), repeat along a new temporal axis, permute to (B, C, T, H, W).
+    Pinned against torchvision itself in tests/test_oracle.py."""
+    x = images_u8.permute(0, 3, 1, 2).contiguous().to(torch.float32).div(255)
+    mean_t = torch.as_tensor(mean, dtype=torch.float32).view(1, 3, 1, 1)
+    std_t = torch.as_tensor(std, dtype=torch.float32).view(1, 3, 1, 1)
+    x = (x - mean_t) / std_t
+    return x.unsqueeze(1).repeat(1, temporal_patch_size, 1, 1, 1).permute(0, 2, 1, 3, 4).contiguous()
+
+
 # ------------------------------------------------------------------------------------------------
 # error metrics (SURVEY.md §7: tensor-normalised max error, cosine)
 # ------------------------------------------------------------------------------------------------

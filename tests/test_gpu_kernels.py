@@ -359,3 +359,18 @@ def test_casts(L):
     x = rnd(100003, seed=70)
     assert torch.equal(L.to_bf16(dev(x)).cpu(), x.to(torch.bfloat16))
     assert torch.equal(L.to_f32(dev(bf(x))).cpu(), bf(x).float())
+
+
+def test_preprocess_u8_bit_exact(L):
+    """uint8 HWC -> normalised (B, C, T, H, W): fp32 output bit-identical to the oracle (= torchvision), bf16 output
+    = that value rounded once; ragged batch of two sizes, T = 1, 2, 4."""
+    g = torch.Generator().manual_seed(11)
+    for (B, H, W, T, mean, std) in [(3, 48, 64, 2, [0.5, 0.5, 0.5], [0.5, 0.5, 0.5]),
+                                    (1, 448, 448, 2, [0.485, 0.456, 0.406], [0.229, 0.224, 0.225]),
+                                    (2, 20, 12, 4, [0.1, 0.2, 0.3], [1.0, 0.7, 0.25]), (1, 16, 16, 1, [0.0] * 3, [1.0] * 3)]:
+        u8 = torch.randint(0, 256, (B, H, W, 3), generator=g, dtype=torch.uint8)
+        ref = VO.preprocess_u8(u8, mean, std, T)
+        got = L.preprocess_u8(dev(u8), mean, std, T, torch.float32)
+        assert got.shape == ref.shape and torch.equal(got.cpu(), ref), (B, H, W, T)
+        gb = L.preprocess_u8(dev(u8), mean, std, T, torch.bfloat16)
+        assert torch.equal(gb.cpu(), ref.to(torch.bfloat16))

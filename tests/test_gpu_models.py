@@ -331,3 +331,30 @@ def test_vision_feature_cache_decode_loop():
         _lib.reset_launch_count()
         vlm.encode_and_fuse(ids.cuda(), pixels2)
         assert _lib.launch_count() > 6
+
+
+def test_uint8_images_through_streamed_encoder():
+    """uint8 HWC uploads -> vf_preprocess_u8 -> tower, through the streaming runtime, equals the
+    tower run on the torchvision-style pixel tensor (bit-exact: same bf16 pixels, same kernels)."""
+    from llm_quest_b200.pipeline import StreamedEncoder
+    from llm_quest_b200.qwen.qwen3_5.preprocess import pixels_from_uint8
+    from llm_quest_b200.qwen.qwen3_5.qwen3_5_vision_model import Qwen3_5VisionModel
+
+    px = 64
+    cfg = qwen_cfg(px, vision_n_layers=2)
+    torch.manual_seed(123)
+    m = Qwen3_5VisionModel(cfg).eval().cuda()
+    mean, std = [0.5, 0.5, 0.5], [0.5, 0.5, 0.5]
+    u8 = torch.randint(0, 256, (4, px, px, 3), generator=torch.Generator().manual_seed(3), dtype=torch.uint8).pin_memory()
+    ref_pixels = VO.preprocess_u8(u8, mean, std, 2).to(torch.bfloat16)
+    with torch.inference_mode():
+        ref = m(ref_pixels.cuda())
+    enc = StreamedEncoder(m, depth=2, pre_fn=lambda d: pixels_from_uint8(d, mean, std, 2))
+    outs = []
+    for _ in range(3):
+        enc.submit(u8)
+        outs += [o.clone() for o in enc.ready()]
+    outs += [o.clone() for o in enc.drain()]
+    assert len(outs) == 3
+    for o in outs:
+        assert torch.equal(o, ref.cpu())

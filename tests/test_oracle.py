@@ -2,6 +2,7 @@
 (oracle/make_golden.py) and against the worked example in the reference docstring."""
 
 import numpy as np
+import pytest
 import torch
 
 from oracle import fusion_oracle as FO
@@ -124,3 +125,22 @@ def test_patch_embed_matmul_equals_conv3d():
 def test_feeds_3d_shape():
     assert FO.feeds_3d_shape((2, 3, 8, 448, 448), 28, 28, 2).tolist() == [[4, 28, 28]]
     assert FO.feeds_3d_shape((2, 1568, 1536), 28, 28, 2).tolist() == [[2, 28, 28]]
+
+
+def test_preprocess_oracle_equals_torchvision():
+    """the oracle's uint8 -> pixel-tensor step is torchvision's to_tensor + normalize + the
+    reference's temporal duplication (qwen3_5_generate_multimodal.py:40-46), bit for bit."""
+    tv = pytest.importorskip("torchvision.transforms.functional")
+    Image = pytest.importorskip("PIL.Image")
+    import numpy as np
+
+    rng = np.random.default_rng(5)
+    arr = rng.integers(0, 256, size=(48, 64, 3), dtype=np.uint8)
+    mean, std = [0.5, 0.5, 0.5], [0.5, 0.5, 0.5]          # config.py QWEN3_5 image_mean / image_std
+    t = tv.normalize(tv.to_tensor(Image.fromarray(arr)), mean=mean, std=std)
+    ref = t.unsqueeze(0).repeat(2, 1, 1, 1).unsqueeze(0).permute(0, 2, 1, 3, 4)
+    got = VO.preprocess_u8(torch.from_numpy(arr)[None], mean, std, 2)
+    assert got.shape == (1, 3, 2, 48, 64) and torch.equal(got, ref)
+    mean, std = [0.485, 0.456, 0.406], [0.229, 0.224, 0.225]   # dataset.py:342
+    t = tv.normalize(tv.to_tensor(Image.fromarray(arr)), mean=mean, std=std)
+    assert torch.equal(VO.preprocess_u8(torch.from_numpy(arr)[None], mean, std, 1)[0, :, 0], t)
