@@ -54,14 +54,13 @@ constexpr int MMA_WARP = NQ * 4 + 1;     // warps 17, 18 (sub-partitions 1, 2): 
 constexpr int Q_TILE_BYTES = 128 * 64 * 2;  // 16 KB
 constexpr int KV_TILE_BYTES = KT * 64 * 2;  // 8 KB
 
-// bit 1 = trace build: block 0 records clock64 stamps per chain and key step into AttnParams::trace
+// FLAGS bit 1 = trace build: block 0 records clock64 stamps per chain and key step into AttnParams::trace
 // (vf_attention_set_trace); diagnosis only, never the default.
 constexpr int ATT_TRACE = 2;
-// bit 2 = lean softmax step: packed f32x2 arithmetic (FFMA2 / FADD2: the softmax warps are bound by issue
+// The softmax step is "lean": packed f32x2 arithmetic (FFMA2 / FADD2: the softmax warps are bound by issue
 // slots, not only by the MUFU) and NO per-step row max: the max of the first key tile stays the reference
 // and a step is redone with a fresh max only when its row sum shows that an exponent ran away (> 2^60).
 // bf16 P and fp32 O/l keep full relative precision at any common scale, so the result is unchanged.
-constexpr int ATT_LEAN = 4;
 constexpr int TRACE_STAMPS = 8;
 
 struct AttnParams {
@@ -73,7 +72,6 @@ struct AttnParams {
   float scale_log2;
   unsigned long long* trace;   // [20 rows][trace_n steps][TRACE_STAMPS] clock64 stamps of block 0, or nullptr
   int trace_first, trace_n;
-  int stagger;     // any-order walkers: one-time start offset between the four chains, in cycles (0 = none)
   __nv_bfloat16* out;
 };
 
@@ -159,14 +157,14 @@ __device__ __forceinline__ void decode_item(const AttnParams& p, int item, int& 
   h = bh - b * p.H;
 }
 
-// FLAGS: bit 0 = the MMA warps walk their two query tiles as INDEPENDENT chains (any-order issue: whichever
-// tile's P is ready is served first) instead of tile 0 then tile 1 of every key step. The in-order walk
-// couples the softmax chains: a chain that runs ahead has to wait for its pair, all four end up in lockstep,
-// compute their exponentials at the same time (sharing the MUFU) and wait for the tensor core at the same
-// time (MUFU idle). Tried and measured slower (round 1): a FIFO token that serialises the exp phases per
-// sub-partition (hand-off latency eats the gain: 2675 vs 2459 us at S=6272), and skipping the exponentials
-// of masked 16-key chunks with a branch inside the unrolled loop (breaks the interleaving).
-constexpr int ATT_ANYORDER = 1;
+// The two MMA warps walk their two query tiles each as INDEPENDENT chains (any-order issue: whichever tile's P
+// is ready is served first) instead of tile 0 then tile 1 of every key step: the in-order walk couples the
+// softmax chains (a chain that runs ahead has to wait for its pair). Measured slower and removed (round 1):
+// a FIFO token that serialises the exp phases per sub-partition (hand-off latency eats the gain: 2675 vs
+// 2459 us at S=6272), a one-time 250-800 cycle stagger of the four chains (2620-2930 vs 2340 us), polling with
+// mbarrier.test_wait instead of the suspending try_wait (2522 vs 2328 us), skipping the exponentials of masked
+// 16-key chunks and running the ragged last query tile on one lane quarter only (no change at S=784: a key
+// step there is bound by the chain's serial latency, not by the amount of exponentials).
 
 template <int FLAGS>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
@@ -195,13 +193,13 @@ attention_kernel(const AttnParams p, const __grid_constant__ CUtensorMap tmQ,
     tma_prefetch_desc(&tmKV);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&q_full[i], 1);
-      mbar_init(&q_empty[i], (FLAGS & ATT_ANYORDER) ? NQ : 2);   // every tile walker / both MMA issuers
+      mbar_init(&q_empty[i], NQ);   // every tile walker
     }
     for (int s = 0; s < KV_STAGES; ++s) {
       mbar_init(&k_full[s], 1);
-      mbar_init(&k_empty[s], (FLAGS & ATT_ANYORDER) ? NQ : 2);
+      mbar_init(&k_empty[s], NQ);
       mbar_init(&v_full[s], 1);
-      mbar_init(&v_empty[s], (FLAGS & ATT_ANYORDER) ? NQ : 2);
+      mbar_init(&v_empty[s], NQ);
     }
     for (int t = 0; t < NQ; ++t) {
       mbar_init(&s_full[t], 1);
@@ -267,10 +265,6 @@ attention_kernel(const AttnParams p, const __grid_constant__ CUtensorMap tmQ,
       const uint64_t v_desc = umma_desc_sw128(smem_u32(smem + AttnSmem::V_OFF));
       constexpr uint64_t QT_DESC = Q_TILE_BYTES >> 4;
       constexpr uint64_t KVT_DESC = KV_TILE_BYTES >> 4;
-      int ks = 0, vs = 0;
-      uint32_t kph = 0, vph = 0, qph = 0;   // qph: bit i = phase of q buffer i
-      int qbuf = 0;
-      uint32_t pph = 0, oeph = 0;   // bit t = phase of p_full[t] / o_empty[t]
 
       auto issue_s_q = [&](int t, int kstage, int qb_) {
         if (elect_one()) {
@@ -301,16 +295,12 @@ attention_kernel(const AttnParams p, const __grid_constant__ CUtensorMap tmQ,
         }
         __syncwarp();
       };
-      auto issue_s = [&](int t, int kstage) { issue_s_q(t, kstage, qbuf); };
-      auto issue_pv_s = [&](int t, int vstage, bool accumulate, bool with_s, int kstage) {
-        issue_pv_s_q(t, vstage, accumulate, with_s, kstage, qbuf);
-      };
       auto commit = [&](uint64_t* bar) {
         if (elect_one()) umma_commit(bar);
         __syncwarp();
       };
 
-      if constexpr (FLAGS & ATT_ANYORDER) {
+      {
         // ---- two independent tile walkers, served in whatever order their barriers complete
         struct Walk {
           ItemIter it;
@@ -381,20 +371,6 @@ attention_kernel(const AttnParams p, const __grid_constant__ CUtensorMap tmQ,
           w.qph = 0; w.kph = 0; w.vph = 0; w.pph = 0; w.oeph = 0; w.done = false;
           next_item(w);
         }
-        // one-time stagger of the four chains (t = 0,2,1,3 start a quarter step apart); the walkers keep
-        // whatever phase offset the chains have, they do not re-align them
-        if (p.stagger > 0) {
-          const long long t_begin = clock64();
-          const int mult0 = (t_lo == 0) ? 0 : 1, mult1 = (t_lo == 0) ? 2 : 3;
-          bool started0 = false, started1 = false;
-          while (!(started0 && started1)) {
-            const long long dt = clock64() - t_begin;
-            if (!started0 && (w0.done || dt >= (long long)mult0 * p.stagger)) started0 = w0.done || advance(w0);
-            if (!started1 && (w1.done || dt >= (long long)mult1 * p.stagger)) started1 = w1.done || advance(w1);
-            if (started0 && !w0.done) advance(w0);
-            if (dt > 4000000000LL) __trap();
-          }
-        }
         long long last = clock64();
         while (!(w0.done && w1.done)) {
           bool prog = false;
@@ -406,52 +382,6 @@ attention_kernel(const AttnParams p, const __grid_constant__ CUtensorMap tmQ,
             __trap();
           }
         }
-      } else {
-      int item;
-      for (ItemIter it(p.n_items); it.next(item);) {
-        int b, h, qb;
-        decode_item(p, item, b, h, qb);
-        int nt = (p.S - qb * (128 * NQ) + 127) / 128;  // query tiles of this item with >= 1 valid row
-        nt = nt > NQ ? NQ : nt;
-        att_wait(&q_full[qbuf], (qph >> qbuf) & 1);
-        const int t_hi = nt < t_lo + 2 ? nt : t_lo + 2;   // tiles [t_lo, t_hi) are mine (maybe none)
-        // prologue: S_t(0). S_t is free as soon as the previous item's last PV_t has retired (in-order
-        // pipe); only the first PV_t of this item has to wait for the warpgroup to drain O_t.
-        att_wait(&k_full[ks], kph);
-        tc_fence_after();
-        for (int t = t_lo; t < t_hi; ++t) {
-          issue_s(t, ks);
-        }
-        commit(&k_empty[ks]);
-        if (p.n_kt == 1) commit(&q_empty[qbuf]);
-        if (++ks == KV_STAGES) { ks = 0; kph ^= 1; }
-
-        for (int j = 0; j < p.n_kt; ++j) {
-          const bool more = (j + 1 < p.n_kt);
-          att_wait(&v_full[vs], vph);
-          if (more) att_wait(&k_full[ks], kph);
-          for (int t = t_lo; t < t_hi; ++t) {
-            att_wait(&p_full[t], (pph >> t) & 1);
-            pph ^= 1u << t;
-            if (j == 0) {  // O_t of the previous item drained?
-              att_wait(&o_empty[t], ((oeph >> t) & 1) ^ 1);
-              oeph ^= 1u << t;
-            }
-            tc_fence_after();
-            issue_pv_s(t, vs, j > 0, more, ks);
-          }
-          commit(&v_empty[vs]);
-          if (++vs == KV_STAGES) { vs = 0; vph ^= 1; }
-          if (more) {
-            commit(&k_empty[ks]);
-            if (j + 2 == p.n_kt) commit(&q_empty[qbuf]);  // the last S MMAs of this item are in flight
-            if (++ks == KV_STAGES) { ks = 0; kph ^= 1; }
-          }
-        }
-        for (int t = t_lo; t < t_hi; ++t) commit(&o_full[t]);
-        qph ^= 1u << qbuf;
-        qbuf ^= 1;
-      }
       }
     }
   } else {
@@ -513,72 +443,41 @@ attention_kernel(const AttnParams p, const __grid_constant__ CUtensorMap tmQ,
             tmem_st_x16(o_addr + c * 16, o);
           }
         };
-        if constexpr (FLAGS & ATT_LEAN) {
-          // P_t = exp2(s*c - m*c) as bf16 pairs over the first 32 columns of S_t; returns the row sum
-          auto exp_store = [&](float mb) {
-            const uint64_t sc2 = pack2(p.scale_log2, p.scale_log2), nb2 = pack2(-mb, -mb);
-            uint64_t acc0 = pack2(0.f, 0.f), acc1 = acc0;
-#pragma unroll
-            for (int c = 0; c < KT / 32; ++c) {
-              uint32_t pk[16];
-#pragma unroll
-              for (int e = 0; e < 16; ++e) {
-                float x0, x1;
-                unpack2(ffma2(pack2(s[c * 32 + 2 * e], s[c * 32 + 2 * e + 1]), sc2, nb2), x0, x1);
-                const float p0 = fast_exp2(x0), p1 = fast_exp2(x1);
-                if (e & 1) acc1 = fadd2(acc1, pack2(p0, p1));
-                else acc0 = fadd2(acc0, pack2(p0, p1));
-                pk[e] = pack_bf16(p0, p1);
-              }
-              tmem_st_x16(s_addr + c * 16, pk);
-            }
-            float a0, a1;
-            unpack2(fadd2(acc0, acc1), a0, a1);
-            return a0 + a1;
-          };
-          if (j == 0) m = row_max();
-          att_trace<FLAGS>(p, warp, gstep, 3);
-          float ssum = exp_store(m * p.scale_log2);
-          // runaway exponent (sum beyond 2^60, inf or NaN) in any row of the warp: redo the step with a fresh max
-          if (j > 0 && __any_sync(0xffffffffu, !(ssum <= 0x1p60f))) {
-            const float mx = row_max();
-            const bool grow = mx > m;
-            const float f = grow ? fast_exp2((m - mx) * p.scale_log2) : 1.0f;
-            if (grow) { m = mx; l *= f; }
-            rescale_o(f);
-            ssum = exp_store(m * p.scale_log2);
-          }
-          l += ssum;
-        } else {
-          const float mx = row_max();
-          if (j == 0) {
-            m = mx;
-          } else {
-            const bool grow = (mx - m) * p.scale_log2 > 8.0f;  // lazy rescale threshold: 2^8 headroom
-            if (__any_sync(0xffffffffu, grow)) {
-              const float f = grow ? fast_exp2((m - mx) * p.scale_log2) : 1.0f;
-              if (grow) { m = mx; l *= f; }
-              rescale_o(f);
-            }
-          }
-          const float mb = m * p.scale_log2;
-          float sum0 = 0.f, sum1 = 0.f;
-          att_trace<FLAGS>(p, warp, gstep, 3);
+        // P_t = exp2(s*c - m*c) as bf16 pairs over the first 32 columns of S_t; returns the row sum
+        auto exp_store = [&](float mb) {
+          const uint64_t sc2 = pack2(p.scale_log2, p.scale_log2), nb2 = pack2(-mb, -mb);
+          uint64_t acc0 = pack2(0.f, 0.f), acc1 = acc0;
 #pragma unroll
           for (int c = 0; c < KT / 32; ++c) {
             uint32_t pk[16];
 #pragma unroll
             for (int e = 0; e < 16; ++e) {
-              const float p0 = fast_exp2(fmaf(s[c * 32 + 2 * e], p.scale_log2, -mb));
-              const float p1 = fast_exp2(fmaf(s[c * 32 + 2 * e + 1], p.scale_log2, -mb));
-              sum0 += p0;
-              sum1 += p1;
+              float x0, x1;
+              unpack2(ffma2(pack2(s[c * 32 + 2 * e], s[c * 32 + 2 * e + 1]), sc2, nb2), x0, x1);
+              const float p0 = fast_exp2(x0), p1 = fast_exp2(x1);
+              if (e & 1) acc1 = fadd2(acc1, pack2(p0, p1));
+              else acc0 = fadd2(acc0, pack2(p0, p1));
               pk[e] = pack_bf16(p0, p1);
             }
-            tmem_st_x16(s_addr + c * 16, pk);   // P_t (bf16 pairs) over the first 32 columns of S_t
+            tmem_st_x16(s_addr + c * 16, pk);
           }
-          l += sum0 + sum1;
+          float a0, a1;
+          unpack2(fadd2(acc0, acc1), a0, a1);
+          return a0 + a1;
+        };
+        if (j == 0) m = row_max();
+        att_trace<FLAGS>(p, warp, gstep, 3);
+        float ssum = exp_store(m * p.scale_log2);
+        // runaway exponent (sum beyond 2^60, inf or NaN) in any row of the warp: redo the step with a fresh max
+        if (j > 0 && __any_sync(0xffffffffu, !(ssum <= 0x1p60f))) {
+          const float mx = row_max();
+          const bool grow = mx > m;
+          const float f = grow ? fast_exp2((m - mx) * p.scale_log2) : 1.0f;
+          if (grow) { m = mx; l *= f; }
+          rescale_o(f);
+          ssum = exp_store(m * p.scale_log2);
         }
+        l += ssum;
         att_trace<FLAGS>(p, warp, gstep, 4);
         tmem_st_wait();
         tc_fence_before();
@@ -667,24 +566,20 @@ extern "C" int vf_attention_fwd(const void* qkv, void* out, int32_t B, int32_t S
   e = encode_tmap(&tmKV, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, qkv, dims, strides, boxkv, CU_TENSOR_MAP_SWIZZLE_128B);
   if (e) return e;
 
-  // development switches: VF_ATTN_FLAGS = variant bits, VF_ATTN_STAGGER = one-time start offset in cycles
-  static int flags = -1, stagger = 0;
+  // VF_ATTN_FLAGS=2 selects the trace build (see vf_attention_set_trace)
+  static int flags = -1;
   if (flags < 0) {
     const char* e_ = getenv("VF_ATTN_FLAGS");
-    const char* s_ = getenv("VF_ATTN_STAGGER");
-    stagger = s_ ? atoi(s_) : 0;
-    flags = e_ ? atoi(e_) & 7 : (ATT_ANYORDER | ATT_LEAN);
+    flags = (e_ && (atoi(e_) & ATT_TRACE)) ? 1 : 0;
   }
-  p.stagger = stagger;
   p.trace = g_trace_buf;
   p.trace_first = g_trace_first;
   p.trace_n = g_trace_n;
   const int sms = device_sm_count();
   VF_REQUIRE(sms > 0, VF_ERR_NO_DEVICE, "no CUDA device");
   using kern_t = void (*)(const AttnParams, const CUtensorMap, const CUtensorMap);
-  static const kern_t kerns[8] = {attention_kernel<0>, attention_kernel<1>, attention_kernel<2>, attention_kernel<3>,
-                                  attention_kernel<4>, attention_kernel<5>, attention_kernel<6>, attention_kernel<7>};
-  static bool configured[8] = {false, false, false, false, false, false, false, false};
+  static const kern_t kerns[2] = {attention_kernel<0>, attention_kernel<ATT_TRACE>};
+  static bool configured[2] = {false, false};
   if (!configured[flags]) {
     VF_CUDA(cudaFuncSetAttribute(kerns[flags], cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem::TOTAL));
     configured[flags] = true;

@@ -1,7 +1,7 @@
 """Dump the in-kernel clock64 trace of vf_attention_fwd (trace build) as text: per key step the phase
 durations of every softmax chain of block 0 and the MMA issue times.
 
-    VF_ATTN_FLAGS=3 python tools/attn_trace.py B S H first_step n_steps
+    VF_ATTN_FLAGS=2 python tools/attn_trace.py B S H first_step n_steps
 """
 import os
 import sys
