@@ -123,6 +123,21 @@ int vf_attention_fwd(const void* qkv, void* out, int32_t B, int32_t S, int32_t H
 int vf_attention_set_trace(void* buf, int32_t first_step, int32_t n_steps);
 
 /* ---------------------------------------------------------------------------------------------
+ * Causal grouped-query attention, head_dim 256, bf16 in/out, fp32 softmax (tcgen05 + TMEM): the attention core
+ * of the first consumer of the fused embeddings and position ids. Replaces
+ *   F.scaled_dot_product_attention(q, k, v, attn_mask=causal, enable_gqa=True) and `ctx * sigmoid(gate)`
+ *   llm_quest/qwen/qwen3_5/qwen3_5_text_model.py:246-262 (prefill: no KV cache, no padding mask)
+ * q: bf16 token-major [B*S, ldq], head h at columns q_col0 + h*q_head_stride .. +256; k, v: [B*S, ldk/ldv], kv head g
+ * at columns 256g; query head h uses kv head h / (Hq/Hkv). out: bf16 [B*S, ldo], head h at columns 256h.
+ * gate (optional, may be NULL): bf16 [B*S, ldg]; out is multiplied by sigmoid(gate[row, gate_col0 +
+ * h*gate_head_stride + d]) before the single bf16 rounding. causal != 0: key t' <= query t inside a sample.
+ * ------------------------------------------------------------------------------------------- */
+int vf_attention_gqa_fwd(const void* q, int64_t ldq, int32_t q_col0, int32_t q_head_stride, const void* k,
+                         int64_t ldk, const void* v, int64_t ldv, void* out, int64_t ldo, const void* gate,
+                         int64_t ldg, int32_t gate_col0, int32_t gate_head_stride, int32_t B, int32_t S, int32_t Hq,
+                         int32_t Hkv, int32_t head_dim, float scale, int32_t causal, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * LayerNorm over the last dim, fp32 or bf16 in, bf16 or fp32 out, fp32 statistics.
  *   variant 0: (x-mean)/sqrt(var+eps)*w+b   nn.LayerNorm    vision_model.py:213-214,229,234,406
  *   variant 1: (x-mean)/(std+eps)*w+b       Part-1 LayerNorm vit_transformer_block.py:21-31
@@ -161,6 +176,13 @@ int vf_mrope_apply(const void* x, void* out, int32_t dtype, int32_t B, int32_t H
                    int32_t hd, const float* cos, const float* sin, int32_t rot, int64_t table_rows,
                    const int64_t* position_ids, int32_t sec_t, int32_t sec_h, int32_t sec_w,
                    const float* norm_weight, float norm_eps, void* stream);
+/* Same, with explicit element strides {batch, head, token} for x and out (multiples of 8): lets q / k be
+ * normalised and rotated IN PLACE inside the token-major output of the w_queries_gate / w_keys projections
+ * (qwen3_5_text_model.py:227-233 without the transposes). x == out is allowed. */
+int vf_mrope_apply_strided(const void* x, void* out, int32_t dtype, int32_t B, int32_t H, int32_t S, int32_t hd,
+                           const int64_t* x_strides, const int64_t* out_strides, const float* cos, const float* sin,
+                           int32_t rot, int64_t table_rows, const int64_t* position_ids, int32_t sec_t, int32_t sec_h,
+                           int32_t sec_w, const float* norm_weight, float norm_eps, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * MRoPE 3-D position ids (bit-exact integer work). Replaces Qwen3_5VLM.compute_3d_position_ids

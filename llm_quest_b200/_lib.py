@@ -27,8 +27,8 @@ VF_EPI_SCATTER_BF16 = 6
 
 EXPORTS = [
     "vf_version", "vf_last_error", "vf_launch_count", "vf_launch_count_reset", "vf_gemm_bf16",
-    "vf_patch_embed", "vf_attention_fwd", "vf_attention_set_trace", "vf_layernorm", "vf_vit_cls_pos", "vf_rope_apply",
-    "vf_mrope_apply", "vf_mrope_position_ids", "vf_fuse_scan", "vf_embed_gather_scatter",
+    "vf_patch_embed", "vf_attention_fwd", "vf_attention_set_trace", "vf_attention_gqa_fwd", "vf_layernorm", "vf_vit_cls_pos", "vf_rope_apply",
+    "vf_mrope_apply", "vf_mrope_apply_strided", "vf_mrope_position_ids", "vf_fuse_scan", "vf_embed_gather_scatter",
     "vf_cast_f32_to_bf16", "vf_cast_bf16_to_f32", "vf_preprocess_u8",
 ]
 
@@ -80,10 +80,14 @@ def lib() -> C.CDLL:
         "vf_patch_embed": [vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, i64, i32, vp, i64, i64, i64, vp],
         "vf_attention_fwd": [vp, vp, i32, i32, i32, f32, vp],
         "vf_attention_set_trace": [vp, i32, i32],
+        "vf_attention_gqa_fwd": [vp, i64, i32, i32, vp, i64, vp, i64, vp, i64, vp, i64, i32, i32, i32, i32, i32, i32, i32,
+                                 f32, i32, vp],
         "vf_layernorm": [vp, i32, i64, vp, vp, vp, i32, i64, i32, f32, i32, i32, i32, i32, vp],
         "vf_vit_cls_pos": [vp, vp, vp, i32, i64, i32, vp],
         "vf_rope_apply": [vp, vp, i32, i32, i32, i32, i32, vp, vp, i32, i64, vp, vp],
         "vf_mrope_apply": [vp, vp, i32, i32, i32, i32, i32, vp, vp, i32, i64, vp, i32, i32, i32, vp, f32, vp],
+        "vf_mrope_apply_strided": [vp, vp, i32, i32, i32, i32, i32, C.POINTER(C.c_int64), C.POINTER(C.c_int64), vp, vp, i32,
+                                   i64, vp, i32, i32, i32, vp, f32, vp],
         "vf_mrope_position_ids": [vp, vp, i64, vp, i32, i32, i32, i32, vp, vp],
         "vf_fuse_scan": [vp, vp, i64, i64, vp, vp, vp, i64, vp, vp],
         "vf_embed_gather_scatter": [vp, vp, i64, i32, vp, i32, i64, vp, vp, i64, i32, vp],
@@ -243,6 +247,21 @@ def attention(qkv, out, B, S, H, scale):
     return out
 
 
+def attention_gqa(q2d, k2d, v2d, out2d, B, S, Hq, Hkv, scale, causal=True, q_col0=0, q_head_stride=256, gate2d=None,
+                  gate_col0=0, gate_head_stride=256):
+    """Causal GQA attention, head_dim 256, on token-major 2-D views (row stride free, unit column stride)."""
+    _require_cuda(q2d, k2d, v2d, out2d, gate2d)
+    for t in (q2d, k2d, v2d, out2d) + ((gate2d,) if gate2d is not None else ()):
+        assert t.dtype == torch.bfloat16 and t.dim() == 2 and t.stride(1) == 1 and t.shape[0] == B * S
+    with _timed("attention_gqa", flops=4.0 * B * Hq * S * S * 256 * (0.5 if causal else 1.0)):
+        check(lib().vf_attention_gqa_fwd(q2d.data_ptr(), q2d.stride(0), q_col0, q_head_stride, k2d.data_ptr(), k2d.stride(0),
+                                         v2d.data_ptr(), v2d.stride(0), out2d.data_ptr(), out2d.stride(0), _p(gate2d),
+                                         gate2d.stride(0) if gate2d is not None else 0, gate_col0, gate_head_stride,
+                                         B, S, Hq, Hkv, 256, float(scale), int(bool(causal)), _stream()),
+              "vf_attention_gqa_fwd")
+    return out2d
+
+
 def layernorm(x2d, w, b, out, eps, variant=0, merge=1, nh=0, nw=0):
     _require_cuda(x2d, w, b, out)
     rows, D = x2d.shape
@@ -292,6 +311,27 @@ def mrope_apply(x, cos, sin, position_ids, mrope_section, norm_weight=None, norm
             "vf_mrope_apply",
         )
     return out
+
+
+def mrope_apply_heads_(x2d, col0, head_stride, B, H, S, cos, sin, position_ids, mrope_section, norm_weight=None,
+                       norm_eps=1e-6, hd=256):
+    """In place on a token-major 2-D tensor [B*S, ld]: head h occupies columns col0 + h*head_stride .. +hd.
+    (q/k zero-centred RMSNorm +) MRoPE-I without any transpose; see vf_mrope_apply_strided."""
+    _require_cuda(x2d, cos, sin, position_ids, norm_weight)
+    assert x2d.dim() == 2 and x2d.stride(1) == 1 and x2d.shape[0] == B * S
+    ld = x2d.stride(0)
+    st = (C.c_int64 * 3)(S * ld, head_stride, ld)
+    pid = position_ids.to(torch.int64).contiguous()
+    st_, sh_, sw_ = (int(v) for v in mrope_section)
+    base = x2d.data_ptr() + col0 * x2d.element_size()
+    with _timed("mrope_apply", bytes=2.0 * B * S * H * hd * x2d.element_size() + 8.0 * pid.numel()):
+        check(
+            lib().vf_mrope_apply_strided(base, base, _DT[x2d.dtype], B, H, S, hd, st, st, cos.data_ptr(), sin.data_ptr(),
+                                         cos.shape[-1], cos.shape[0], pid.data_ptr(), st_, sh_, sw_, _p(norm_weight),
+                                         float(norm_eps), _stream()),
+            "vf_mrope_apply_strided",
+        )
+    return x2d
 
 
 def mrope_position_ids(input_ids, image_mask, image_token_id, feeds_cpu, merge):

@@ -1,0 +1,467 @@
+// vf_attention_gqa.cu — causal grouped-query attention, head_dim 256, for sm_100a (bf16, fp32 softmax).
+//
+// The attention core of the first consumer of the fused embeddings and MRoPE-I position ids, the text model's
+// MRoPEGatedAttention in prefill (reference llm_quest/qwen/qwen3_5/qwen3_5_text_model.py:194-267):
+//     F.scaled_dot_product_attention(q, k, v, causal mask, enable_gqa=True)   8 query heads / 2 kv heads x 256
+//     ctx = ctx * sigmoid(gate)                                               (:262)
+// q, k, v are read token-major ([B*S, heads*256], the layout the projection GEMMs write) through TMA boxes at
+// the head's column offset; the context is written token-major, already multiplied by sigmoid(gate) when a gate
+// pointer is given (the gate columns live next to the query columns in the w_queries_gate output, :235-238).
+//
+// At head_dim 256 the balance is the opposite of the vision kernel (vf_attention.cu): a 128 x 64 score tile costs
+// 1024 tensor cycles (QK^T over K=256 + PV over N=256) against 512 MUFU cycles, so ONE chain per CTA is enough if
+// the tensor core never waits for the softmax:
+//   TMEM (384 of 512 columns): S double-buffered at [0,64) / [64,128); P(j) overwrites S(j) in its buffer;
+//                              O at [128,384).
+//   warps 0..3  softmax, one thread per query row (lean step: packed f32x2 math, first-tile max as reference,
+//               step redone with a fresh max only when a row sum runs past 2^60 — see vf_attention.cu);
+//   warp 4      TMA loader: Q (4 swizzle atoms of 64 dims) once per item, K and V tiles through 2-stage rings;
+//   warp 5      MMA issuer: S(j+1) = Q K_{j+1}^T is issued BEFORE waiting for P(j), so it runs under the softmax of
+//               step j; then O += P(j) V_j. One thread's MMAs retire in order, which makes the S/P aliasing safe.
+// Work item = (sample, query head, 128-row query tile), causal: key tiles 0 .. 2*tile+1 only; items are walked in
+// decreasing cost (last query tiles first), boustrophedon over the CTAs.
+#include "vf_common.cuh"
+
+#include <math.h>
+
+namespace vf {
+
+constexpr int GD = 256;                      // head dim
+constexpr int GKT = 64;                      // keys per tile
+constexpr int G_ATOMS = GD / 64;             // 128-byte swizzle atoms per row
+constexpr int G_THREADS = 192;
+constexpr int G_STAGES = 2;
+constexpr int GQ_ATOM_BYTES = 128 * 128;     // 128 rows x 64 dims
+constexpr int GKV_ATOM_BYTES = GKT * 128;    // 64 keys x 64 dims
+constexpr int GQ_BYTES = G_ATOMS * GQ_ATOM_BYTES;     // 64 KB
+constexpr int GKV_BYTES = G_ATOMS * GKV_ATOM_BYTES;   // 32 KB
+constexpr int GT_S = 0, GT_O = 128;          // TMEM columns
+
+struct GqaParams {
+  int B, S, Hq, Hkv;
+  int n_qt, n_items, n_bh;
+  int causal;
+  float scale_log2;
+  __nv_bfloat16* out;
+  long long ldo;
+  const __nv_bfloat16* gate;   // optional: out *= sigmoid(gate[row, gate_col0 + h*gate_head_stride + d])
+  long long ldg;
+  int gate_col0, gate_head_stride;
+  int q_col0, q_head_stride;   // column of head h in the q tensor map = q_col0 + h*q_head_stride
+};
+
+struct GqaSmem {
+  static constexpr int Q_OFF = 0;
+  static constexpr int K_OFF = GQ_BYTES;
+  static constexpr int V_OFF = K_OFF + G_STAGES * GKV_BYTES;
+  static constexpr int BAR_OFF = V_OFF + G_STAGES * GKV_BYTES;
+  static constexpr int TOTAL = BAR_OFF + 256 + 1024;
+};
+
+// MN-major SW128 operand spanning several 64-element atoms along N: atoms `lbo_bytes` apart, 8-row (K) groups 1024 B
+__device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(lbo_bytes >> 4) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
+struct GqaItem {
+  int b, h, kvh, qt, n_kt;
+};
+__device__ __forceinline__ GqaItem gqa_decode(const GqaParams& p, int item) {
+  GqaItem it;
+  const int r = item / p.n_bh;
+  const int bh = item - r * p.n_bh;
+  it.qt = p.n_qt - 1 - r;                      // expensive (late) query tiles first
+  it.b = bh / p.Hq;
+  it.h = bh - it.b * p.Hq;
+  it.kvh = it.h / (p.Hq / p.Hkv);
+  const int all = (p.S + GKT - 1) / GKT;
+  const int need = 2 * it.qt + 2;              // key tiles that reach the diagonal of this query tile
+  it.n_kt = (p.causal && need < all) ? need : all;
+  return it;
+}
+
+struct GqaIter {   // same boustrophedon walk as vf_attention.cu
+  int r, n;
+  __device__ explicit GqaIter(int n_items) : r(0), n(n_items) {}
+  __device__ __forceinline__ bool next(int& item) {
+    const int G = gridDim.x;
+    while (r * G < n) {
+      const int k = (r & 1) ? G - 1 - static_cast<int>(blockIdx.x) : static_cast<int>(blockIdx.x);
+      const int idx = r * G + k;
+      ++r;
+      if (idx < n) { item = idx; return true; }
+    }
+    return false;
+  }
+};
+
+__global__ void __launch_bounds__(G_THREADS, 1)
+attention_gqa_kernel(const GqaParams p, const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                     const __grid_constant__ CUtensorMap tmV) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + GqaSmem::BAR_OFF);
+  uint64_t* q_full = bars;                 // [1]
+  uint64_t* q_empty = bars + 1;            // [1]
+  uint64_t* k_full = bars + 2;             // [G_STAGES]
+  uint64_t* k_empty = k_full + G_STAGES;
+  uint64_t* v_full = k_empty + G_STAGES;
+  uint64_t* v_empty = v_full + G_STAGES;
+  uint64_t* s_full = v_empty + G_STAGES;   // [2] per S buffer
+  uint64_t* p_full = s_full + 2;           // [2]
+  uint64_t* pv_done = p_full + 2;          // [1] completes once per PV
+  uint64_t* o_full = pv_done + 1;          // [1]
+  uint64_t* o_empty = o_full + 1;          // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_empty + 1);
+  const char* const WHO = "vf_attention_gqa";
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(q_full, 1);
+    mbar_init(q_empty, 1);
+    for (int s = 0; s < G_STAGES; ++s) {
+      mbar_init(&k_full[s], 1);
+      mbar_init(&k_empty[s], 1);
+      mbar_init(&v_full[s], 1);
+      mbar_init(&v_empty[s], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 4);
+    }
+    mbar_init(pv_done, 1);
+    mbar_init(o_full, 1);
+    mbar_init(o_empty, 4);
+    fence_barrier_init();
+  }
+  if (warp == 5) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 4) {
+    // -------------------------------------------------------------------- TMA loader
+    if (lane == 0) {
+      int ks = 0, vs = 0;
+      uint32_t kph = 0, vph = 0, qph = 0;
+      int item;
+      for (GqaIter it(p.n_items); it.next(item);) {
+        const GqaItem w = gqa_decode(p, item);
+        const int row0 = w.b * p.S;
+        mbar_wait_or_trap(q_empty, qph ^ 1, WHO);
+        mbar_expect_tx(q_full, GQ_BYTES);
+#pragma unroll
+        for (int a = 0; a < G_ATOMS; ++a)
+          tma_load_2d(smem + GqaSmem::Q_OFF + a * GQ_ATOM_BYTES, &tmQ, q_full, p.q_col0 + w.h * p.q_head_stride + a * 64,
+                      row0 + w.qt * 128);
+        qph ^= 1;
+        for (int j = 0; j < w.n_kt; ++j) {
+          mbar_wait_or_trap(&k_empty[ks], kph ^ 1, WHO);
+          mbar_expect_tx(&k_full[ks], GKV_BYTES);
+#pragma unroll
+          for (int a = 0; a < G_ATOMS; ++a)
+            tma_load_2d(smem + GqaSmem::K_OFF + ks * GKV_BYTES + a * GKV_ATOM_BYTES, &tmK, &k_full[ks],
+                        w.kvh * GD + a * 64, row0 + j * GKT);
+          if (++ks == G_STAGES) { ks = 0; kph ^= 1; }
+          mbar_wait_or_trap(&v_empty[vs], vph ^ 1, WHO);
+          mbar_expect_tx(&v_full[vs], GKV_BYTES);
+#pragma unroll
+          for (int a = 0; a < G_ATOMS; ++a)
+            tma_load_2d(smem + GqaSmem::V_OFF + vs * GKV_BYTES + a * GKV_ATOM_BYTES, &tmV, &v_full[vs],
+                        w.kvh * GD + a * 64, row0 + j * GKT);
+          if (++vs == G_STAGES) { vs = 0; vph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // -------------------------------------------------------------------- MMA issuer
+    constexpr uint32_t idesc_s = umma_idesc_bf16(128, GKT, 0, 0);
+    constexpr uint32_t idesc_o = umma_idesc_bf16(128, GD, 0, 1);   // N = 256: V is MN-major, four 64-dim atoms (LBO)
+    const uint32_t q_addr = smem_u32(smem + GqaSmem::Q_OFF);
+    const uint32_t k_addr = smem_u32(smem + GqaSmem::K_OFF);
+    const uint32_t v_addr = smem_u32(smem + GqaSmem::V_OFF);
+    int ks = 0, vs = 0;
+    uint32_t kph = 0, vph = 0, qph = 0, oeph = 0;
+    unsigned g = 0;   // global key-step counter: S buffer = g & 1, barrier parity = (g >> 1) & 1
+    auto issue_s = [&](unsigned gs, int kstage) {
+      if (elect_one()) {
+        const uint32_t d = tmem_base + GT_S + (gs & 1) * 64;
+#pragma unroll
+        for (int kk = 0; kk < GD / 16; ++kk) {
+          const int a = kk >> 2, i = kk & 3;
+          umma_ss(d, umma_desc_sw128(q_addr + a * GQ_ATOM_BYTES) + 2 * i,
+                  umma_desc_sw128(k_addr + kstage * GKV_BYTES + a * GKV_ATOM_BYTES) + 2 * i, idesc_s, kk != 0);
+        }
+        umma_commit(&s_full[gs & 1]);
+        umma_commit(&k_empty[kstage]);
+      }
+      __syncwarp();
+    };
+    int item;
+    for (GqaIter it(p.n_items); it.next(item);) {
+      const GqaItem w = gqa_decode(p, item);
+      mbar_wait_or_trap(q_full, qph, WHO); qph ^= 1;
+      mbar_wait_or_trap(&k_full[ks], kph, WHO);
+      tc_fence_after();
+      issue_s(g, ks);
+      if (++ks == G_STAGES) { ks = 0; kph ^= 1; }
+      for (int j = 0; j < w.n_kt; ++j, ++g) {
+        if (j + 1 < w.n_kt) {   // S(j+1) runs under the softmax of step j
+          mbar_wait_or_trap(&k_full[ks], kph, WHO);
+          tc_fence_after();
+          issue_s(g + 1, ks);
+          if (++ks == G_STAGES) { ks = 0; kph ^= 1; }
+        } else if (elect_one()) {
+          umma_commit(q_empty);   // every S of this item has been issued
+        }
+        __syncwarp();
+        mbar_wait_or_trap(&v_full[vs], vph, WHO);
+        mbar_wait_or_trap(&p_full[g & 1], (g >> 1) & 1, WHO);
+        if (j == 0) { mbar_wait_or_trap(o_empty, oeph ^ 1, WHO); oeph ^= 1; }
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t a_t = tmem_base + GT_S + (g & 1) * 64;
+#pragma unroll
+          for (int k_ = 0; k_ < GKT / 16; ++k_) {   // 16 keys per MMA: 8 TMEM columns of bf16 pairs / 16 V rows
+            umma_ts(tmem_base + GT_O, a_t + k_ * 8,
+                    umma_desc_sw128_mn(v_addr + vs * GKV_BYTES, GKV_ATOM_BYTES) + k_ * (2048 >> 4), idesc_o,
+                    j > 0 || k_ != 0);
+          }
+          umma_commit(&v_empty[vs]);
+          umma_commit(pv_done);
+          if (j + 1 == w.n_kt) umma_commit(o_full);
+        }
+        __syncwarp();
+        if (++vs == G_STAGES) { vs = 0; vph ^= 1; }
+      }
+    }
+  } else {
+    // -------------------------------------------------------------------- softmax warps (one thread per query row)
+    const uint32_t lane_sel = static_cast<uint32_t>(warp * 32) << 16;
+    const uint32_t o_addr = tmem_base + lane_sel + GT_O;
+    unsigned g = 0;
+    uint32_t oph = 0;
+    int item;
+    for (GqaIter it(p.n_items); it.next(item);) {
+      const GqaItem w = gqa_decode(p, item);
+      const int q_pos = w.qt * 128 + warp * 32 + lane;        // position of my row inside the sample
+      float m = -INFINITY, l = 0.f;
+      if (p.gate && q_pos < p.S) {   // the epilogue's gate row (512 B) is pulled into L2 while the item runs
+        const char* gp = reinterpret_cast<const char*>(p.gate + (static_cast<long long>(w.b) * p.S + q_pos) * p.ldg +
+                                                       p.gate_col0 + w.h * p.gate_head_stride);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) asm volatile("prefetch.global.L2 [%0];" ::"l"(gp + i * 128));
+      }
+      for (int j = 0; j < w.n_kt; ++j, ++g) {
+        const uint32_t s_addr = tmem_base + lane_sel + GT_S + (g & 1) * 64;
+        mbar_wait_or_trap(&s_full[g & 1], (g >> 1) & 1, WHO);
+        tc_fence_after();
+        float s[GKT];
+        tmem_ld_x32(s_addr, reinterpret_cast<uint32_t*>(s));
+        tmem_ld_x32(s_addr + 32, reinterpret_cast<uint32_t*>(s) + 32);
+        tmem_ld_wait();
+        // keys [0, limit] of this tile are visible to my row: sequence end and, if causal, the diagonal
+        int limit = p.S - 1 - j * GKT;
+        if (p.causal && q_pos - j * GKT < limit) limit = q_pos - j * GKT;
+        if (__any_sync(0xffffffffu, limit < GKT - 1)) {
+#pragma unroll
+          for (int c = 0; c < GKT; ++c)
+            if (c > limit) s[c] = -INFINITY;
+        }
+        auto row_max = [&]() {
+          float mx0 = fmaxf(s[0], s[1]), mx1 = fmaxf(s[2], s[3]);
+#pragma unroll
+          for (int c = 4; c < GKT; c += 2) {
+            mx0 = fmaxf(mx0, s[c]);
+            mx1 = fmaxf(mx1, s[c + 1]);
+          }
+          return fmaxf(mx0, mx1);
+        };
+        auto exp_store = [&](float mb) {
+          const uint64_t sc2 = pack2(p.scale_log2, p.scale_log2), nb2 = pack2(-mb, -mb);
+          uint64_t acc0 = pack2(0.f, 0.f), acc1 = acc0;
+#pragma unroll
+          for (int c = 0; c < GKT / 32; ++c) {
+            uint32_t pk[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              float x0, x1;
+              unpack2(ffma2(pack2(s[c * 32 + 2 * e], s[c * 32 + 2 * e + 1]), sc2, nb2), x0, x1);
+              const float p0 = fast_exp2(x0), p1 = fast_exp2(x1);
+              if (e & 1) acc1 = fadd2(acc1, pack2(p0, p1));
+              else acc0 = fadd2(acc0, pack2(p0, p1));
+              pk[e] = pack_bf16(p0, p1);
+            }
+            tmem_st_x16(s_addr + c * 16, pk);   // P(j) over the first 32 columns of its S buffer
+          }
+          float a0, a1;
+          unpack2(fadd2(acc0, acc1), a0, a1);
+          return a0 + a1;
+        };
+        if (j == 0) m = row_max();               // key 0 is visible to every row, so m is finite
+        float ssum = exp_store(m * p.scale_log2);
+        if (j > 0 && __any_sync(0xffffffffu, !(ssum <= 0x1p60f))) {   // runaway exponent: redo with a fresh max
+          mbar_wait_or_trap(pv_done, (g - 1) & 1, WHO);                // O is stable once PV(previous step) retired
+          tc_fence_after();
+          const float mx = row_max();
+          const bool grow = mx > m;
+          const float f = grow ? fast_exp2((m - mx) * p.scale_log2) : 1.0f;
+          if (grow) { m = mx; l *= f; }
+#pragma unroll
+          for (int c = 0; c < GD / 16; ++c) {
+            uint32_t o[16];
+            tmem_ld_x16(o_addr + c * 16, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 16; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * f);
+            tmem_st_x16(o_addr + c * 16, o);
+          }
+          ssum = exp_store(m * p.scale_log2);
+        }
+        l += ssum;
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[g & 1]);
+      }
+      // ---- item epilogue: O / l (* sigmoid(gate)) -> global, 32 columns at a time
+      mbar_wait_or_trap(o_full, oph, WHO); oph ^= 1;
+      tc_fence_after();
+      const float inv = 1.0f / l;
+      const bool row_ok = q_pos < p.S;
+      const long long row = static_cast<long long>(w.b) * p.S + q_pos;
+      __nv_bfloat16* orow = p.out + row * p.ldo + w.h * GD;
+      const __nv_bfloat16* grow_ = p.gate ? p.gate + row * p.ldg + p.gate_col0 + w.h * p.gate_head_stride : nullptr;
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {     // 128 columns at a time: the row's gate values are requested together
+        uint4 gq[16];
+        if (grow_ && row_ok) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) gq[i] = __ldg(reinterpret_cast<const uint4*>(grow_ + half * 128) + i);
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t o[32];
+          tmem_ld_x32(o_addr + half * 128 + c * 32, o);
+          tmem_ld_wait();
+          if (row_ok) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              float v[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(o[q * 8 + e]) * inv;
+              if (grow_) {
+                const uint4 g4 = gq[c * 4 + q];
+                const uint32_t gw[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {   // sigmoid(x) = 0.5 tanh(x/2) + 0.5: one MUFU op per element
+                  v[2 * e] *= fmaf(0.5f, fast_tanh(0.5f * bf16_lo(gw[e])), 0.5f);
+                  v[2 * e + 1] *= fmaf(0.5f, fast_tanh(0.5f * bf16_hi(gw[e])), 0.5f);
+                }
+              }
+              reinterpret_cast<uint4*>(orow + half * 128 + c * 32)[q] =
+                  make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+            }
+          }
+          __syncwarp();
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(o_empty);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+}  // namespace vf
+
+using namespace vf;
+
+extern "C" int vf_attention_gqa_fwd(const void* q, int64_t ldq, int32_t q_col0, int32_t q_head_stride, const void* k,
+                                    int64_t ldk, const void* v, int64_t ldv, void* out, int64_t ldo, const void* gate,
+                                    int64_t ldg, int32_t gate_col0, int32_t gate_head_stride, int32_t B, int32_t S,
+                                    int32_t Hq, int32_t Hkv, int32_t head_dim, float scale, int32_t causal,
+                                    void* stream) {
+  VF_REQUIRE(q && k && v && out, VF_ERR_ARG, "vf_attention_gqa_fwd: null pointer");
+  VF_REQUIRE(B > 0 && S > 0 && Hq > 0 && Hkv > 0 && Hq % Hkv == 0, VF_ERR_ARG,
+             "vf_attention_gqa_fwd: bad shape B=%d S=%d Hq=%d Hkv=%d", B, S, Hq, Hkv);
+  VF_REQUIRE(head_dim == GD, VF_ERR_ARG, "vf_attention_gqa_fwd: head_dim %d unsupported (256)", head_dim);
+  VF_REQUIRE((long long)B * S < (1ll << 31), VF_ERR_ARG, "vf_attention_gqa_fwd: B*S too large");
+  VF_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0 && (!gate || ldg % 8 == 0) && q_col0 % 8 == 0 &&
+                 q_head_stride % 8 == 0 && gate_col0 % 8 == 0 && gate_head_stride % 8 == 0,
+             VF_ERR_ALIGN, "vf_attention_gqa_fwd: row pitches and column offsets must be multiples of 8 elements");
+  VF_REQUIRE(((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v) |
+               reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(gate)) & 15) == 0,
+             VF_ERR_ALIGN, "vf_attention_gqa_fwd: pointers must be 16-byte aligned");
+  VF_REQUIRE(q_col0 + (long long)(Hq - 1) * q_head_stride + GD <= ldq && (long long)Hkv * GD <= ldk &&
+                 (long long)Hkv * GD <= ldv && (long long)Hq * GD <= ldo,
+             VF_ERR_ARG, "vf_attention_gqa_fwd: heads do not fit the row pitch");
+
+  GqaParams p{};
+  p.B = B; p.S = S; p.Hq = Hq; p.Hkv = Hkv;
+  p.n_qt = (S + 127) / 128;
+  p.n_bh = B * Hq;
+  p.n_items = p.n_bh * p.n_qt;
+  p.causal = causal ? 1 : 0;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  p.out = reinterpret_cast<__nv_bfloat16*>(out);
+  p.ldo = ldo;
+  p.gate = reinterpret_cast<const __nv_bfloat16*>(gate);
+  p.ldg = ldg; p.gate_col0 = gate_col0; p.gate_head_stride = gate_head_stride;
+  p.q_col0 = q_col0; p.q_head_stride = q_head_stride;
+
+  CUtensorMap tmQ, tmK, tmV;
+  const uint64_t rows = (uint64_t)B * S;
+  {
+    uint64_t dims[2] = {(uint64_t)ldq, rows};
+    uint64_t strides[1] = {(uint64_t)ldq * 2};
+    uint32_t box[2] = {64, 128};
+    int e = encode_tmap(&tmQ, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, q, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (e) return e;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)ldk, rows};
+    uint64_t strides[1] = {(uint64_t)ldk * 2};
+    uint32_t box[2] = {64, GKT};
+    int e = encode_tmap(&tmK, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, k, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (e) return e;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)ldv, rows};
+    uint64_t strides[1] = {(uint64_t)ldv * 2};
+    uint32_t box[2] = {64, GKT};
+    int e = encode_tmap(&tmV, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, v, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (e) return e;
+  }
+  const int sms = device_sm_count();
+  VF_REQUIRE(sms > 0, VF_ERR_NO_DEVICE, "no CUDA device");
+  const int grid = p.n_items < sms ? p.n_items : sms;
+  static bool configured = false;
+  if (!configured) {
+    VF_CUDA(cudaFuncSetAttribute(attention_gqa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GqaSmem::TOTAL));
+    configured = true;
+  }
+  attention_gqa_kernel<<<grid, G_THREADS, GqaSmem::TOTAL, static_cast<cudaStream_t>(stream)>>>(p, tmQ, tmK, tmV);
+  count_launch();
+  VF_CUDA(cudaGetLastError());
+  return VF_OK;
+}

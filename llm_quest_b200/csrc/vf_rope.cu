@@ -141,8 +141,8 @@ struct LaneRaw {
 // Lane l owns elements [l*EPL, (l+1)*EPL) of a row, EPL = hd/32 (4 or 8).
 template <typename T, int EPL>
 __global__ void __launch_bounds__(256)
-mrope_apply_kernel(const T* __restrict__ x, T* __restrict__ out, int B, int H, int S,
-                   const float* __restrict__ cos, const float* __restrict__ sin, int rot,
+mrope_apply_kernel(const T* x, T* out, int B, int H, int S, long long xs_b, long long xs_h, long long xs_s,
+                   long long os_b, long long os_h, long long os_s, const float* __restrict__ cos, const float* __restrict__ sin, int rot,
                    const long long* __restrict__ position_ids, int sec_h, int sec_w,
                    const float* __restrict__ norm_w, float norm_eps) {
   constexpr int HD = EPL * 32;
@@ -181,13 +181,15 @@ mrope_apply_kernel(const T* __restrict__ x, T* __restrict__ out, int B, int H, i
     for (int q = 0; q < EPL / 4; ++q) Ld4<float>::ld(norm_w + lane * EPL + q * 4, *reinterpret_cast<float(*)[4]>(&w[q * 4]));
   }
 
-  const long long head_stride = static_cast<long long>(S) * HD;
-  const long long base = (b * H * S + s) * HD + lane * EPL;
+  // element strides (batch, head, token) of x and out: [B,H,S,hd] contiguous, or head columns of a token-major
+  // projection output; x == out (in place) is fine, a row is read completely before it is written
+  const long long xbase = b * xs_b + s * xs_s + lane * EPL;
+  const long long obase = b * os_b + s * os_s + lane * EPL;
   for (int h0 = 0; h0 < H; h0 += HC) {
     LaneRaw<T, EPL> raw[HC];
 #pragma unroll
     for (int i = 0; i < HC; ++i)
-      if (h0 + i < H) raw[i].load(x + base + (h0 + i) * head_stride);
+      if (h0 + i < H) raw[i].load(x + xbase + (h0 + i) * xs_h);
 #pragma unroll
     for (int i = 0; i < HC; ++i) {
       if (h0 + i >= H) break;
@@ -217,7 +219,7 @@ mrope_apply_kernel(const T* __restrict__ x, T* __restrict__ out, int B, int H, i
         }
       }
       raw[i].pack(v);
-      raw[i].store(out + base + (h0 + i) * head_stride);
+      raw[i].store(out + obase + (h0 + i) * os_h);
     }
   }
 }
@@ -258,12 +260,12 @@ extern "C" int vf_rope_apply(const void* x, void* out, int32_t dtype, int32_t B,
   return VF_OK;
 }
 
-extern "C" int vf_mrope_apply(const void* x, void* out, int32_t dtype, int32_t B, int32_t H, int32_t S,
-                              int32_t hd, const float* cos, const float* sin, int32_t rot,
-                              int64_t table_rows, const int64_t* position_ids, int32_t sec_t,
-                              int32_t sec_h, int32_t sec_w, const float* norm_weight, float norm_eps,
-                              void* stream) {
-  VF_REQUIRE(x && out && cos && sin && position_ids, VF_ERR_ARG, "vf_mrope_apply: null pointer");
+extern "C" int vf_mrope_apply_strided(const void* x, void* out, int32_t dtype, int32_t B, int32_t H, int32_t S,
+                                      int32_t hd, const int64_t* x_strides, const int64_t* out_strides,
+                                      const float* cos, const float* sin, int32_t rot, int64_t table_rows,
+                                      const int64_t* position_ids, int32_t sec_t, int32_t sec_h, int32_t sec_w,
+                                      const float* norm_weight, float norm_eps, void* stream) {
+  VF_REQUIRE(x && out && cos && sin && position_ids && x_strides && out_strides, VF_ERR_ARG, "vf_mrope_apply: null pointer");
   VF_REQUIRE(B > 0 && H > 0 && S > 0, VF_ERR_ARG, "vf_mrope_apply: bad shape");
   VF_REQUIRE(hd == 128 || hd == 256, VF_ERR_ARG, "vf_mrope_apply: head_dim %d unsupported (128 or 256)", hd);
   VF_REQUIRE(rot > 0 && rot <= hd && (rot / 2) % (hd / 32) == 0, VF_ERR_ARG,
@@ -274,12 +276,16 @@ extern "C" int vf_mrope_apply(const void* x, void* out, int32_t dtype, int32_t B
   VF_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
                  (reinterpret_cast<uintptr_t>(norm_weight) & 15) == 0,
              VF_ERR_ALIGN, "vf_mrope_apply: pointers must be 16-byte aligned");
+  for (int i = 0; i < 3; ++i)
+    VF_REQUIRE(x_strides[i] % 8 == 0 && out_strides[i] % 8 == 0, VF_ERR_ALIGN,
+               "vf_mrope_apply: strides must be multiples of 8 elements");
   const long long tokens = (long long)B * S;
   const unsigned grid = (unsigned)((tokens + 7) / 8);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const long long* pid = reinterpret_cast<const long long*>(position_ids);
-#define VF_MROPE(T, EPL)                                                                           \
-  mrope_apply_kernel<T, EPL><<<grid, 256, 0, s>>>((const T*)x, (T*)out, B, H, S, cos, sin, rot, pid, \
+#define VF_MROPE(T, EPL)                                                                                          \
+  mrope_apply_kernel<T, EPL><<<grid, 256, 0, s>>>((const T*)x, (T*)out, B, H, S, x_strides[0], x_strides[1], x_strides[2], \
+                                                  out_strides[0], out_strides[1], out_strides[2], cos, sin, rot, pid,     \
                                                   sec_h, sec_w, norm_weight, norm_eps)
   if (dtype == 0 && hd == 256) VF_MROPE(float, 8);
   else if (dtype == 0 && hd == 128) VF_MROPE(float, 4);
@@ -293,4 +299,14 @@ extern "C" int vf_mrope_apply(const void* x, void* out, int32_t dtype, int32_t B
   count_launch();
   VF_CUDA(cudaGetLastError());
   return VF_OK;
+}
+
+extern "C" int vf_mrope_apply(const void* x, void* out, int32_t dtype, int32_t B, int32_t H, int32_t S,
+                              int32_t hd, const float* cos, const float* sin, int32_t rot,
+                              int64_t table_rows, const int64_t* position_ids, int32_t sec_t,
+                              int32_t sec_h, int32_t sec_w, const float* norm_weight, float norm_eps,
+                              void* stream) {
+  const int64_t st[3] = {(int64_t)H * S * hd, (int64_t)S * hd, hd};   // [B, H, S, hd] contiguous
+  return vf_mrope_apply_strided(x, out, dtype, B, H, S, hd, st, st, cos, sin, rot, table_rows, position_ids, sec_t, sec_h,
+                                sec_w, norm_weight, norm_eps, stream);
 }

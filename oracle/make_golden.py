@@ -258,6 +258,47 @@ def make_rope_and_merge():
     torch.save(out, GOLD / "rope_merge.pt")
 
 
+def make_text_attention():
+    """First consumer of the ids and fused embeddings: MRoPEGatedAttention in prefill."""
+    from llm_quest.common.buffers import GlobalBuffers
+    from llm_quest.qwen.qwen3_5.qwen3_5_text_model import MRoPEGatedAttention
+
+    cfg = {"emb_dim": 256, "n_heads": 4, "num_kv_groups": 2, "head_dim": 256, "dtype": torch.float32, "p_dropout": 0.0,
+           "training": False, "mrope_section": [11, 11, 10]}
+    torch.manual_seed(123)
+    att = MRoPEGatedAttention(cfg, layer_idx=0).eval()
+    with torch.no_grad():
+        att.q_norm.scale.copy_(0.1 * torch.randn(256))
+        att.k_norm.scale.copy_(0.1 * torch.randn(256))
+    round_module_(att)
+    b, seq = 2, 150
+    g = torch.Generator().manual_seed(77)
+    x = bf16_exact(torch.randn(b, seq, 256, generator=g))
+    # multimodal-looking ids: text, a 2x(4x6) image block, text (axes differ inside the block)
+    ids = torch.randint(0, 1000, (b, seq), generator=g)
+    ids[:, 20:20 + 12] = IMG
+    ids[1, 80:80 + 12] = IMG
+    pid = torch.from_numpy(FO.mrope_position_ids(ids.numpy(), [[2, 4, 6], [2, 4, 6]], None, IMG, 2))
+    cos, sin = GlobalBuffers.get_rope_params(512, 10_000_000, 256, rotation_factor=0.25)
+    mask = ~GlobalBuffers.get_causal_mask(512)
+    with torch.inference_mode():
+        ref = att(x, mask, cos, sin, position_ids=pid)
+        ref_1d = att(x, mask, cos, sin, position_ids=torch.arange(seq).expand(3, b, seq))
+    sd = {k: v.detach().clone() for k, v in att.state_dict().items()}
+    oc, os_ = VO.text_rope_tables(512, 10_000_000, 256, 0.25)
+    assert torch.equal(oc, cos) and torch.equal(os_, sin)
+    got = VO.mrope_gated_attention_forward(sd, cfg, x, cos, sin, pid)
+    err = VO.max_norm_err(got, ref)
+    assert err <= 2e-5, err
+    assert VO.max_norm_err(VO.mrope_gated_attention_forward(sd, cfg, x, cos, sin, None), ref_1d) <= 2e-5
+    print(f"MRoPEGatedAttention prefill: oracle vs reference max_norm_err={err:.2e}")
+    # weights and x are bf16-exact: stored as bf16 to keep the fixture small (tests cast back to fp32)
+    sd = {k: v.to(torch.bfloat16) for k, v in sd.items()}
+    torch.save({"cfg": {k: v for k, v in cfg.items() if k != "dtype"}, "state_dict": sd, "x": x.to(torch.bfloat16), "position_ids": pid,
+                "expected": ref.clone(), "expected_1d": ref_1d.clone(), "rope": {"ctx": 512, "base": 10_000_000, "factor": 0.25}},
+               GOLD / "text_attention.pt")
+
+
 if __name__ == "__main__":
     GOLD.mkdir(parents=True, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
@@ -265,5 +306,6 @@ if __name__ == "__main__":
     make_rope_and_merge()
     make_qwen_tower()
     make_vit()
+    make_text_attention()
     for f in sorted(GOLD.glob("*.pt")):
         print(f"{f.name}: {f.stat().st_size / 1024:.0f} KiB")

@@ -253,6 +253,33 @@ def vit_adapter_forward(sd: dict, x: torch.Tensor):
     return y + sd["adapter.3.bias"] if "adapter.3.bias" in sd else y
 
 
+def mrope_gated_attention_forward(sd: dict, cfg: dict, x, cos, sin, position_ids=None):
+    """MRoPEGatedAttention.forward in prefill (qwen3_5_text_model.py:206-267; no KV cache, no padding mask):
+    fused q|gate projection split per head (:216-219), k / v projections, zero-centred RMSNorm on q and k
+    (qwen3_next_attention.py:41-46), MRoPE-I (rope.py:297-358), causal grouped-query SDPA (:252-260), sigmoid
+    gate (:262), out_proj. sd keys: w_queries_gate.weight, w_keys.weight, w_values.weight, q_norm.scale,
+    k_norm.scale, out_proj.weight."""
+    b, seq, _ = x.shape
+    H, G, hd = cfg["n_heads"], cfg["num_kv_groups"], cfg["head_dim"]
+    qg = (x @ sd["w_queries_gate.weight"].t()).view(b, seq, H, 2 * hd)
+    q, gate = qg[..., :hd], qg[..., hd:]
+    k = (x @ sd["w_keys.weight"].t()).view(b, seq, G, hd).transpose(1, 2)
+    v = (x @ sd["w_values.weight"].t()).view(b, seq, G, hd).transpose(1, 2)
+    q = zero_centered_rmsnorm(q.transpose(1, 2), sd["q_norm.scale"])
+    k = zero_centered_rmsnorm(k, sd["k_norm.scale"])
+    if position_ids is None:
+        position_ids = torch.arange(seq).expand(3, b, seq)
+    q = mrope_apply(q, cos, sin, position_ids, cfg["mrope_section"])
+    k = mrope_apply(k, cos, sin, position_ids, cfg["mrope_section"])
+    rep = H // G
+    kk, vv = k.repeat_interleave(rep, dim=1), v.repeat_interleave(rep, dim=1)
+    att = (q @ kk.transpose(-1, -2)) * hd**-0.5
+    att = att.masked_fill(torch.triu(torch.ones(seq, seq, dtype=torch.bool), diagonal=1), float("-inf"))
+    ctx = (torch.softmax(att, dim=-1) @ vv).transpose(1, 2).reshape(b, seq, H * hd)
+    ctx = ctx * torch.sigmoid(gate.reshape(b, seq, H * hd))
+    return ctx @ sd["out_proj.weight"].t()
+
+
 def preprocess_u8(images_u8: torch.Tensor, mean, std, temporal_patch_size: int = 2) -> torch.Tensor:
     """uint8 [B, H, W, 3] -> fp32 [B, 3, T, H, W], the pre-processing that feeds PatchEmbedding3D
     (qwen3_5_generate_multimodal.py:40-46 after the resize): torchvision to_tensor (HWC -> CHW, / 255),

@@ -47,3 +47,8 @@ def golden_qwen():
 @pytest.fixture(scope="session")
 def golden_vit():
     return load_golden("vit_tiny.pt")
+
+
+@pytest.fixture(scope="session")
+def golden_text_attention():
+    return torch.load(GOLDEN / "text_attention.pt", map_location="cpu", weights_only=True)

@@ -374,3 +374,67 @@ def test_preprocess_u8_bit_exact(L):
         assert got.shape == ref.shape and torch.equal(got.cpu(), ref), (B, H, W, T)
         gb = L.preprocess_u8(dev(u8), mean, std, T, torch.bfloat16)
         assert torch.equal(gb.cpu(), ref.to(torch.bfloat16))
+
+
+# ------------------------------------------------------------------------------------------------
+# consumer side: causal GQA attention head_dim 256, in-place strided MRoPE
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,S,Hq,Hkv,causal,gate", [(2, 100, 8, 2, True, True), (1, 128, 4, 2, True, False),
+                                                     (2, 300, 8, 2, True, True), (1, 257, 2, 1, False, False),
+                                                     (1, 1000, 4, 4, True, True), (3, 64, 8, 2, True, True)])
+def test_attention_gqa(L, B, S, Hq, Hkv, causal, gate):
+    qg = bf(rnd(B * S, Hq * 512, seed=31))              # per head: 256 query columns, then 256 gate columns
+    k, v = bf(rnd(B * S, Hkv * 256, seed=32)), bf(rnd(B * S, Hkv * 256, seed=33))
+    out = torch.zeros((B * S, Hq * 256), dtype=torch.bfloat16, device="cuda")
+    dq = dev(qg)
+    L.attention_gqa(dq, dev(k), dev(v), out, B, S, Hq, Hkv, 256 ** -0.5, causal, q_col0=0, q_head_stride=512,
+                    gate2d=dq if gate else None, gate_col0=256, gate_head_stride=512)
+    x = qg.float().view(B, S, Hq, 512)
+    q4, g4 = x[..., :256].transpose(1, 2), x[..., 256:]
+    k4 = k.float().view(B, S, Hkv, 256).transpose(1, 2).repeat_interleave(Hq // Hkv, dim=1)
+    v4 = v.float().view(B, S, Hkv, 256).transpose(1, 2).repeat_interleave(Hq // Hkv, dim=1)
+    att = (q4 @ k4.transpose(-1, -2)) / 16.0
+    if causal:
+        att = att.masked_fill(torch.triu(torch.ones(S, S, dtype=torch.bool), diagonal=1), float("-inf"))
+    ref = (torch.softmax(att, dim=-1) @ v4).transpose(1, 2)
+    if gate:
+        ref = ref * torch.sigmoid(g4)
+    check_close(out, ref.reshape(B * S, Hq * 256), tol=6e-3, what=f"gqa attention B{B} S{S} Hq{Hq}/{Hkv} causal={causal} gate={gate}")
+
+
+def test_attention_gqa_large_scores_redo_path(L):
+    """Scores that grow along the sequence force the runaway-sum redo (fresh max + O rescale) in later key tiles."""
+    B, S, Hq, Hkv = 1, 320, 2, 1
+    q = rnd(B * S, Hq * 256, seed=41) * 0.2
+    k = rnd(B * S, Hkv * 256, seed=42) * 0.2
+    k[200:] += 40.0 * q[200:201, :256].sign()          # late keys align with the queries: exponents jump by > 2^60
+    q[:, :256] = q[:, :256].abs() * 8
+    q, k, v = bf(q), bf(k), bf(rnd(B * S, Hkv * 256, seed=43))
+    out = torch.zeros((B * S, Hq * 256), dtype=torch.bfloat16, device="cuda")
+    L.attention_gqa(dev(q), dev(k), dev(v), out, B, S, Hq, Hkv, 256 ** -0.5, True)
+    q4 = q.float().view(B, S, Hq, 256).transpose(1, 2)
+    k4 = k.float().view(B, S, Hkv, 256).transpose(1, 2).repeat_interleave(Hq, dim=1)
+    v4 = v.float().view(B, S, Hkv, 256).transpose(1, 2).repeat_interleave(Hq, dim=1)
+    att = ((q4 @ k4.transpose(-1, -2)) / 16.0).masked_fill(torch.triu(torch.ones(S, S, dtype=torch.bool), diagonal=1), float("-inf"))
+    assert float(att[att > -1e30].max() - att[0, 0, 250, 0]) * 1.4427 > 64      # the test really exercises the redo
+    ref = (torch.softmax(att, dim=-1) @ v4).transpose(1, 2).reshape(B * S, Hq * 256)
+    check_close(out, ref, tol=8e-3, what="gqa attention redo path")
+
+
+def test_mrope_strided_in_place_equals_contiguous(L, golden_rope):
+    """q/k heads normalised + rotated in place inside a token-major projection buffer == the [B,H,S,hd] kernel."""
+    from llm_quest_b200.common.rope import RoPE
+
+    B, H, S, hd = 2, 4, 37, 256
+    cos, sin = VO.text_rope_tables(512, 10_000_000, 256, 0.25)
+    pid = torch.randint(0, 400, (3, B, S), generator=torch.Generator().manual_seed(3))
+    w = (1.0 + 0.1 * rnd(256, seed=8)).float()
+    buf = bf(rnd(B * S, 64 + H * 512, seed=9))           # heads at columns 64 + h*512 (gate-like padding between them)
+    heads = buf[:, 64:].view(B, S, H, 512)[..., :256].permute(0, 2, 1, 3).contiguous()
+    ref = RoPE.apply_mrope(dev(heads), dev(cos), dev(sin), dev(pid), (11, 11, 10), norm_weight=dev(w))
+    d = dev(buf)
+    L.mrope_apply_heads_(d, 64, 512, B, H, S, dev(cos), dev(sin), dev(pid), (11, 11, 10), dev(w), 1e-6, 256)
+    got = d[:, 64:].view(B, S, H, 512)[..., :256].permute(0, 2, 1, 3)
+    assert torch.equal(got.cpu(), ref.cpu())
+    untouched = d.cpu()[:, 64:].view(B, S, H, 512)[..., 256:]
+    assert torch.equal(untouched, buf[:, 64:].view(B, S, H, 512)[..., 256:]) and torch.equal(d.cpu()[:, :64], buf[:, :64])

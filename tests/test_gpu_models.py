@@ -358,3 +358,28 @@ def test_uint8_images_through_streamed_encoder():
     assert len(outs) == 3
     for o in outs:
         assert torch.equal(o, ref.cpu())
+
+
+def test_mrope_gated_attention_prefill_golden(golden_text_attention):
+    """the drop-in MRoPEGatedAttention (prefill) against the output of the live reference module
+    (fp32, CPU) on the committed fixture: multimodal position ids and the text-only (1-D) case."""
+    from llm_quest_b200.common.rope import RoPE
+    from llm_quest_b200.qwen.qwen3_5.qwen3_5_text_model import MRoPEGatedAttention
+
+    g = golden_text_attention
+    cfg = dict(g["cfg"], dtype=torch.float32)
+    att = MRoPEGatedAttention(cfg, layer_idx=0).eval()
+    assert set(att.state_dict().keys()) == set(g["state_dict"].keys())
+    att.load_state_dict({k: v.float() for k, v in g["state_dict"].items()})
+    att = att.cuda()
+    r = g["rope"]
+    cos, sin = RoPE.compute_angles(r["base"], cfg["head_dim"], r["ctx"], rotation_factor=r["factor"])
+    x = g["x"].float().cuda()
+    with torch.inference_mode():
+        out = att(x, None, cos, sin, position_ids=g["position_ids"].cuda())
+        out1 = att(x, None, cos, sin)
+    assert out.dtype == torch.float32 and out.shape == g["expected"].shape
+    check_close(out, g["expected"], "MRoPEGatedAttention prefill (multimodal ids) vs reference")
+    check_close(out1, g["expected_1d"], "MRoPEGatedAttention prefill (text-only ids) vs reference")
+    with pytest.raises(Exception, match="prefill"):
+        att(x, None, cos, sin, cache=object())

@@ -144,3 +144,15 @@ def test_preprocess_oracle_equals_torchvision():
     mean, std = [0.485, 0.456, 0.406], [0.229, 0.224, 0.225]   # dataset.py:342
     t = tv.normalize(tv.to_tensor(Image.fromarray(arr)), mean=mean, std=std)
     assert torch.equal(VO.preprocess_u8(torch.from_numpy(arr)[None], mean, std, 1)[0, :, 0], t)
+
+
+def test_text_attention_golden(golden_text_attention):
+    """the oracle's MRoPEGatedAttention prefill against the output of the live reference module."""
+    g = golden_text_attention
+    sd = {k: v.float() for k, v in g["state_dict"].items()}
+    cfg, r = g["cfg"], g["rope"]
+    cos, sin = VO.text_rope_tables(r["ctx"], r["base"], cfg["head_dim"], r["factor"])
+    got = VO.mrope_gated_attention_forward(sd, cfg, g["x"].float(), cos, sin, g["position_ids"])
+    assert VO.max_norm_err(got, g["expected"]) <= 2e-5
+    got = VO.mrope_gated_attention_forward(sd, cfg, g["x"].float(), cos, sin, None)
+    assert VO.max_norm_err(got, g["expected_1d"]) <= 2e-5

@@ -158,9 +158,35 @@ def mrope():
     emit("mrope_apply", "q [32,8,2832,256] + k [32,2,2832,256] bf16: zero-centred RMSNorm + MRoPE-I (one layer's worth)", ms, b, 0.0, fam)
 
 
+def textattn():
+    """cfg-3 consumer: MRoPEGatedAttention prefill on the fused embeddings [32, 2832, 1024] with the MRoPE-I ids."""
+    from llm_quest_b200.common.rope import RoPE
+    from llm_quest_b200.qwen.qwen3_5.qwen3_5_text_model import MRoPEGatedAttention
+
+    cfg = {"emb_dim": 1024, "n_heads": 8, "num_kv_groups": 2, "head_dim": 256, "dtype": torch.bfloat16, "p_dropout": 0.0,
+           "training": False, "mrope_section": [11, 11, 10]}
+    torch.manual_seed(123)
+    att = MRoPEGatedAttention(cfg, layer_idx=3).eval().to(DEV)
+    b, seq = 32, 2832
+    g = torch.Generator().manual_seed(99)
+    x = torch.randn(b, seq, 1024, generator=g).to(torch.bfloat16).to(DEV)
+    pid = torch.randint(0, 2104, (3, b, seq), generator=g).to(DEV)
+    cos, sin = RoPE.compute_angles(10_000_000, 256, 8192, rotation_factor=0.25)
+    cos, sin = cos.to(DEV), sin.to(DEV)
+    fn = lambda: att(x, None, cos, sin, position_ids=pid)
+    with torch.inference_mode():
+        ms = timed(fn, 10)
+        fam = families(fn)
+    M = b * seq
+    flops = 2.0 * M * 1024 * 5120 + 2.0 * M * 2048 * 1024 + 4.0 * b * 8 * seq * seq * 256 * 0.5
+    emit("text_attention_prefill", "MRoPEGatedAttention prefill, one layer: batch 32 x seq 2832, 8 q / 2 kv heads x 256 "
+         "(fused q|gate|k|v GEMM, in-place RMSNorm+MRoPE-I, causal GQA attention with sigmoid gate, out_proj)", ms, b, flops, fam,
+         {"tokens_per_s": round(M / (ms / 1e3), 1)})
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["cfg3", "cfg3native", "cfg4", "cfg5", "mrope"]
+    which = sys.argv[1:] or ["cfg3", "cfg3native", "cfg4", "cfg5", "mrope", "textattn"]
     _lib.lib()
     for w in which:
-        {"cfg3": lambda: cfg3(False), "cfg3native": lambda: cfg3(True), "cfg4": cfg4, "cfg5": cfg5, "mrope": mrope}[w]()
+        {"cfg3": lambda: cfg3(False), "cfg3native": lambda: cfg3(True), "cfg4": cfg4, "cfg5": cfg5, "mrope": mrope, "textattn": textattn}[w]()
         torch.cuda.empty_cache()
