@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-./tools_gpu_first.sh "$@"
+./tools/gpu_first.sh "$@"
 timeout 900 python bench.py --steps 10 --warmup 3 --no-cpu > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench exit=$?"
 python - <<'PY'
 import json
