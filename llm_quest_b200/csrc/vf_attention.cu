@@ -69,6 +69,8 @@ struct AttnParams {
   int n_kt;        // ceil(S / KT)
   int n_items;     // B * H * n_qblk
   int n_bh;        // B * H
+  int pair;        // S <= 256 (at most two query tiles): an item is a PAIR of (sample, head) — chains 0,1 run the
+                   // first, chains 2,3 the second, each with its own 2-stage K/V ring (all four chains stay busy)
   float scale_log2;
   unsigned long long* trace;   // [20 rows][trace_n steps][TRACE_STAMPS] clock64 stamps of block 0, or nullptr
   int trace_first, trace_n;
@@ -132,6 +134,12 @@ __device__ __forceinline__ void decode_item(const AttnParams& p, int item, int& 
   h = bh - b * p.H;
 }
 
+// Pair mode: (sample, head) index of member m (0 or 1) of an item, or -1 when the last item has no second member.
+__device__ __forceinline__ int pair_bh(const AttnParams& p, int item, int m) {
+  const int bh = 2 * item + m;
+  return bh < p.n_bh ? bh : -1;
+}
+
 // The two MMA warps walk their two query tiles each as INDEPENDENT chains (any-order issue: whichever tile's P
 // is ready is served first) instead of tile 0 then tile 1 of every key step: the in-order walk couples the
 // softmax chains (a chain that runs ahead has to wait for its pair). Measured slower and removed (round 1):
@@ -172,9 +180,9 @@ attention_kernel(const AttnParams p, const __grid_constant__ CUtensorMap tmQ,
     }
     for (int s = 0; s < KV_STAGES; ++s) {
       mbar_init(&k_full[s], 1);
-      mbar_init(&k_empty[s], NQ);
+      mbar_init(&k_empty[s], p.pair ? 2 : NQ);   // the walkers that consume the stage
       mbar_init(&v_full[s], 1);
-      mbar_init(&v_empty[s], NQ);
+      mbar_init(&v_empty[s], p.pair ? 2 : NQ);
     }
     for (int t = 0; t < NQ; ++t) {
       mbar_init(&s_full[t], 1);
@@ -202,6 +210,39 @@ attention_kernel(const AttnParams p, const __grid_constant__ CUtensorMap tmQ,
         uint32_t kph = 0, vph = 0, qph = 0;   // qph: bit i = phase of q buffer i
         int qbuf = 0;
         int item;
+        if (p.pair) {
+          // ring m (stages 2m, 2m+1) belongs to member m; ks/vs/kph/vph hold one 2-bit-wide lane per ring
+          int kst[2] = {0, 0}, vst[2] = {0, 0};
+          uint32_t kp[2] = {0, 0}, vp[2] = {0, 0};
+          for (ItemIter it(p.n_items); it.next(item);) {
+            att_wait(&q_empty[qbuf], ((qph >> qbuf) & 1) ^ 1);
+            mbar_expect_tx(&q_full[qbuf], NQ * Q_TILE_BYTES);
+            for (int t = 0; t < NQ; ++t) {
+              int bh = pair_bh(p, item, t >> 1);
+              if (bh < 0) bh = 2 * item;          // no second member: the tiles are loaded but never used
+              tma_load_2d(smem + AttnSmem::Q_OFF + (qbuf * NQ + t) * Q_TILE_BYTES, &tmQ, &q_full[qbuf], (bh % p.H) * 64,
+                          (bh / p.H) * p.S + (t & 1) * 128);
+            }
+            qph ^= 1u << qbuf;
+            qbuf ^= 1;
+            for (int j = 0; j < p.n_kt; ++j) {
+              for (int m = 0; m < 2; ++m) {
+                const int bh = pair_bh(p, item, m);
+                if (bh < 0) continue;
+                const int row0 = (bh / p.H) * p.S, h = bh % p.H;
+                const int sk = 2 * m + kst[m], sv = 2 * m + vst[m];
+                att_wait(&k_empty[sk], kp[m] ^ 1);
+                mbar_expect_tx(&k_full[sk], KV_TILE_BYTES);
+                tma_load_2d(smem + AttnSmem::K_OFF + sk * KV_TILE_BYTES, &tmKV, &k_full[sk], p.H * 64 + h * 64, row0 + j * KT);
+                if (++kst[m] == 2) { kst[m] = 0; kp[m] ^= 1; }
+                att_wait(&v_empty[sv], vp[m] ^ 1);
+                mbar_expect_tx(&v_full[sv], KV_TILE_BYTES);
+                tma_load_2d(smem + AttnSmem::V_OFF + sv * KV_TILE_BYTES, &tmKV, &v_full[sv], 2 * p.H * 64 + h * 64, row0 + j * KT);
+                if (++vst[m] == 2) { vst[m] = 0; vp[m] ^= 1; }
+              }
+            }
+          }
+        } else
         for (ItemIter it(p.n_items); it.next(item);) {
           int b, h, qb;
           decode_item(p, item, b, h, qb);
@@ -280,6 +321,8 @@ attention_kernel(const AttnParams p, const __grid_constant__ CUtensorMap tmQ,
         struct Walk {
           ItemIter it;
           int t, nt, j, qbuf, ks, vs;          // j = -1: S(t,0) of the current item is the next action
+          int base, depth;                     // K/V ring of this walker: stages [base, base + depth)
+          bool member;                         // pair mode: the walker's (sample, head) exists in this item
           uint32_t qph, kph, vph, pph, oeph;   // qph: bit i = phase of q buffer i
           bool done;
           int gstep;
@@ -288,16 +331,31 @@ attention_kernel(const AttnParams p, const __grid_constant__ CUtensorMap tmQ,
         auto next_item = [&](Walk& w) {
           int item;
           if (!w.it.next(item)) { w.done = true; return; }
-          int b_, h_, qb_;
-          decode_item(p, item, b_, h_, qb_);
-          int nt = (p.S - qb_ * (128 * NQ) + 127) / 128;
-          w.nt = nt > NQ ? NQ : nt;
+          if (p.pair) {
+            w.member = pair_bh(p, item, w.t >> 1) >= 0;
+            w.nt = (p.S + 127) / 128;          // tiles per member (1 or 2); the walker's tile inside it is t & 1
+          } else {
+            int b_, h_, qb_;
+            decode_item(p, item, b_, h_, qb_);
+            int nt = (p.S - qb_ * (128 * NQ) + 127) / 128;
+            w.nt = nt > NQ ? NQ : nt;
+            w.member = true;
+          }
           w.j = -1;
         };
         // one action of walker w if everything it needs has arrived; never blocks
         auto advance = [&](Walk& w) -> bool {
           const int t = w.t;
-          const bool mine = t < w.nt;          // tiles beyond the item's last query tile only recycle K/V slots
+          // tiles beyond the item's last query tile only recycle K/V slots
+          const bool mine = (p.pair ? (t & 1) : t) < w.nt;
+          if (!w.member) {                     // pair mode, last item without a second member: only release the Q buffer
+            if (!mbar_try_wait(&q_full[w.qbuf], (w.qph >> w.qbuf) & 1)) return false;
+            commit(&q_empty[w.qbuf]);
+            w.qph ^= 1u << w.qbuf;
+            w.qbuf ^= 1;
+            next_item(w);
+            return true;
+          }
           if (w.j < 0) {
             if (!mbar_try_wait(&q_full[w.qbuf], (w.qph >> w.qbuf) & 1)) return false;
             if (!mbar_try_wait(&k_full[w.ks], w.kph)) return false;
@@ -305,7 +363,7 @@ attention_kernel(const AttnParams p, const __grid_constant__ CUtensorMap tmQ,
             if (mine) issue_s_q(t, w.ks, w.qbuf);
             commit(&k_empty[w.ks]);
             if (p.n_kt == 1) commit(&q_empty[w.qbuf]);
-            if (++w.ks == KV_STAGES) { w.ks = 0; w.kph ^= 1; }
+            if (++w.ks == w.base + w.depth) { w.ks = w.base; w.kph ^= 1; }
             w.j = 0;
             return true;
           }
@@ -324,11 +382,11 @@ attention_kernel(const AttnParams p, const __grid_constant__ CUtensorMap tmQ,
             ++w.gstep;
           }
           commit(&v_empty[w.vs]);
-          if (++w.vs == KV_STAGES) { w.vs = 0; w.vph ^= 1; }
+          if (++w.vs == w.base + w.depth) { w.vs = w.base; w.vph ^= 1; }
           if (more) {
             commit(&k_empty[w.ks]);
             if (w.j + 2 == p.n_kt) commit(&q_empty[w.qbuf]);
-            if (++w.ks == KV_STAGES) { w.ks = 0; w.kph ^= 1; }
+            if (++w.ks == w.base + w.depth) { w.ks = w.base; w.kph ^= 1; }
             ++w.j;
           } else {
             if (mine) commit(&o_full[t]);
@@ -342,7 +400,10 @@ attention_kernel(const AttnParams p, const __grid_constant__ CUtensorMap tmQ,
         Walk* ws[2] = {&w0, &w1};
         for (int i = 0; i < 2; ++i) {
           Walk& w = *ws[i];
-          w.t = t_lo + i; w.qbuf = 0; w.ks = 0; w.vs = 0;
+          w.t = t_lo + i; w.qbuf = 0;
+          w.base = p.pair ? 2 * (w.t >> 1) : 0;
+          w.depth = p.pair ? 2 : KV_STAGES;
+          w.ks = w.base; w.vs = w.base;
           w.qph = 0; w.kph = 0; w.vph = 0; w.pph = 0; w.oeph = 0; w.done = false;
           next_item(w);
         }
@@ -373,10 +434,20 @@ attention_kernel(const AttnParams p, const __grid_constant__ CUtensorMap tmQ,
 
     int item;
     for (ItemIter it(p.n_items); it.next(item);) {
-      int b, h, qb;
-      decode_item(p, item, b, h, qb);
-      if (qb * (128 * NQ) + t * 128 >= p.S) continue;  // whole tile out of range (uniform per warp)
-      const int q_in_sample = qb * (128 * NQ) + t * 128 + r_local;
+      int b, h, tile_row0;
+      if (p.pair) {   // chains 0,1 -> member 0, chains 2,3 -> member 1; tile inside the member = t & 1
+        const int bh = pair_bh(p, item, t >> 1);
+        tile_row0 = (t & 1) * 128;
+        if (bh < 0 || tile_row0 >= p.S) continue;
+        b = bh / p.H;
+        h = bh - b * p.H;
+      } else {
+        int qb;
+        decode_item(p, item, b, h, qb);
+        tile_row0 = qb * (128 * NQ) + t * 128;
+        if (tile_row0 >= p.S) continue;                // whole tile out of range (uniform per warp)
+      }
+      const int q_in_sample = tile_row0 + r_local;
 
       float m = -INFINITY;   // running (possibly stale) row max, raw score units
       float l = 0.f;         // running row sum
@@ -529,6 +600,12 @@ extern "C" int vf_attention_fwd(const void* qkv, void* out, int32_t B, int32_t S
   p.n_kt = (S + KT - 1) / KT;
   p.n_bh = B * H;
   p.n_items = p.n_bh * p.n_qblk;
+  const int sms = device_sm_count();
+  VF_REQUIRE(sms > 0, VF_ERR_NO_DEVICE, "no CUDA device");
+  // at most two query tiles per (sample, head): two of them share an item — once there are more (sample, head)
+  // pairs than SMs (below that, pairing would only leave SMs idle)
+  p.pair = (S <= 256 && p.n_bh > sms) ? 1 : 0;
+  if (p.pair) p.n_items = (p.n_bh + 1) / 2;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
   CUtensorMap tmQ, tmKV;
@@ -550,8 +627,6 @@ extern "C" int vf_attention_fwd(const void* qkv, void* out, int32_t B, int32_t S
   p.trace = g_trace_buf;
   p.trace_first = g_trace_first;
   p.trace_n = g_trace_n;
-  const int sms = device_sm_count();
-  VF_REQUIRE(sms > 0, VF_ERR_NO_DEVICE, "no CUDA device");
   using kern_t = void (*)(const AttnParams, const CUtensorMap, const CUtensorMap);
   static const kern_t kerns[2] = {attention_kernel<0>, attention_kernel<ATT_TRACE>};
   static bool configured[2] = {false, false};

@@ -100,7 +100,19 @@ __device__ __forceinline__ float gelu_tanh_f(float x) {
   return fmaf(h, t, h);
 }
 __device__ __forceinline__ float gelu_erf_f(float x) {
-  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
+  // x * Phi(x) with Phi from the Abramowitz-Stegun 7.1.26 form of erfc: q = 0.5 * poly(t) * exp(-x^2/2), t = 1/(1 + p|x|/sqrt2),
+  // Phi = q for x < 0 and 1 - q otherwise. |error| < 5e-7 on GELU (three orders below the bf16 rounding of the output),
+  // branch-free, 2 MUFU + 10 FMA-pipe ops; erff() costs ~30 instructions with a divergent branch and made the erf-GELU
+  // epilogue issue-bound (777 vs 1288 TF for the tanh-GELU GEMM of the same shape).
+  const float ax = fabsf(x) * 0.70710678118654752f;
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, ax, 1.0f)));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float q = 0.5f * poly * t * fast_exp2(-ax * ax * 1.4426950408889634f);
+  return x * (x < 0.f ? q : 1.0f - q);
 }
 
 template <int EPI, int BN, bool PATCH, int CG>

@@ -24,6 +24,42 @@ from collections import deque
 import torch
 
 
+class GraphedEncoder:
+    """Small-batch latency path: the tower's ~75 launches captured once in a CUDA graph and replayed.
+
+    At batch 1-8 a forward is launch-bound (each kernel runs for a few microseconds); every libvfuse call takes raw
+    pointers and a stream, allocates nothing and never synchronises, so the whole forward is capturable as is: the
+    tensor maps are kernel parameters encoded at capture time against the graph's private buffers. Inputs are copied
+    into the captured input buffer, the output buffer is returned (valid until the next call).
+
+        g = GraphedEncoder(model, example_pixels)     # example fixes shape and dtype
+        out = g(pixels)                               # same values as model(pixels), bit for bit
+    """
+
+    def __init__(self, model: torch.nn.Module, example: torch.Tensor, warmup: int = 2):
+        if not example.is_cuda:
+            raise RuntimeError("GraphedEncoder needs CUDA tensors (libvfuse has no CPU fallback)")
+        self.model = model
+        self.static_in = example.clone()
+        side = torch.cuda.Stream(example.device)
+        side.wait_stream(torch.cuda.current_stream(example.device))
+        with torch.cuda.stream(side), torch.inference_mode():
+            for _ in range(warmup):          # builds the packed-weight caches outside the capture
+                model(self.static_in)
+        torch.cuda.current_stream(example.device).wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.inference_mode(), torch.cuda.graph(self.graph):
+            self.static_out = model(self.static_in)
+
+    def __call__(self, pixels: torch.Tensor) -> torch.Tensor:
+        if pixels.shape != self.static_in.shape or pixels.dtype != self.static_in.dtype:
+            raise ValueError(f"captured for {tuple(self.static_in.shape)} {self.static_in.dtype}, "
+                             f"got {tuple(pixels.shape)} {pixels.dtype}")
+        self.static_in.copy_(pixels, non_blocking=True)
+        self.graph.replay()
+        return self.static_out
+
+
 class StreamedEncoder:
     def __init__(self, model: torch.nn.Module, depth: int = 2, device: torch.device | None = None, post_fn=None,
                  pre_fn=None):

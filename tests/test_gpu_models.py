@@ -383,3 +383,23 @@ def test_mrope_gated_attention_prefill_golden(golden_text_attention):
     check_close(out1, g["expected_1d"], "MRoPEGatedAttention prefill (text-only ids) vs reference")
     with pytest.raises(Exception, match="prefill"):
         att(x, None, cos, sin, cache=object())
+
+
+def test_graphed_encoder_matches_eager():
+    """CUDA-graph replay of the tower (small-batch latency path): identical bits, new inputs honoured."""
+    from llm_quest_b200.pipeline import GraphedEncoder
+    from llm_quest_b200.qwen.qwen3_5.qwen3_5_vision_model import Qwen3_5VisionModel
+
+    torch.manual_seed(123)
+    m = Qwen3_5VisionModel(qwen_cfg(224, vision_n_layers=3)).eval().cuda()
+    g = torch.Generator().manual_seed(9)
+    xs = [torch.randn(2, 3, 2, 224, 224, generator=g).to(torch.bfloat16).cuda() for _ in range(3)]
+    with torch.inference_mode():
+        refs = [m(x).clone() for x in xs]
+    ge = GraphedEncoder(m, xs[0])
+    for x, r in zip(xs + xs[:1], refs + refs[:1]):
+        out = ge(x)
+        torch.cuda.synchronize()
+        assert torch.equal(out, r)
+    with pytest.raises(ValueError):
+        ge(xs[0][:1])

@@ -158,6 +158,41 @@ def mrope():
     emit("mrope_apply", "q [32,8,2832,256] + k [32,2,2832,256] bf16: zero-centred RMSNorm + MRoPE-I (one layer's worth)", ms, b, 0.0, fam)
 
 
+def cfg1():
+    """cfg-1: Part-1 ViT-B/16 classifier, 224x224, batch 8 (the reference's own CPU-runnable case) + batch 256."""
+    from llm_quest_b200.multimodal.vision_transformer.vit_model import ViTModel
+
+    cfg = {"img_width": 224, "img_height": 224, "patch_size": 16, "num_channels": 3, "emb_dim": 768, "n_layers": 12,
+           "n_heads": 12, "drop_rate": 0.1, "qkv_bias": True, "num_classes": 100}
+    torch.manual_seed(123)
+    m = ViTModel(cfg).eval().to(DEV)
+    flops_img = 2 * 196 * 768 * 768 + 12 * (2 * 197 * 768 * 2304 + 4 * 197 * 197 * 768 + 2 * 197 * 768 * 768 + 4 * 197 * 768 * 3072) + 2 * 768 * 100
+    for B in (8, 256):
+        x = torch.randn(B, 3, 224, 224, generator=torch.Generator().manual_seed(1234)).to(DEV)
+        fn = lambda: m(x)
+        with torch.inference_mode():
+            ms = timed(fn, 10)
+            fam = families(fn)
+        emit(f"cfg1_b{B}", f"Part-1 ViT-B/16 classifier forward, 224x224, batch {B}, fp32 parameters / bf16 operands", ms, B,
+             flops_img * B, fam)
+
+
+def latency():
+    """Small-batch latency of the Qwen tower at 448x448: eager launches vs CUDA-graph replay (pipeline.GraphedEncoder)."""
+    from llm_quest_b200.pipeline import GraphedEncoder
+
+    model, _ = tower(448)
+    for B in (1, 4):
+        x = torch.randn(B, 3, 2, 448, 448, generator=torch.Generator().manual_seed(1234)).to(torch.bfloat16).to(DEV)
+        with torch.inference_mode():
+            ms_eager = timed(lambda: model(x), 20)
+        ge = GraphedEncoder(model, x)
+        ms_graph = timed(lambda: ge(x), 20)
+        print(json.dumps({"config": f"latency_b{B}", "workload": f"Qwen3-ViT tower 448x448, batch {B}: ms per forward",
+                          "ms_eager": round(ms_eager, 3), "ms_cuda_graph": round(ms_graph, 3),
+                          "images_per_s_graph": round(B / (ms_graph / 1e3), 1)}), flush=True)
+
+
 def textattn():
     """cfg-3 consumer: MRoPEGatedAttention prefill on the fused embeddings [32, 2832, 1024] with the MRoPE-I ids."""
     from llm_quest_b200.common.rope import RoPE
@@ -185,8 +220,8 @@ def textattn():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["cfg3", "cfg3native", "cfg4", "cfg5", "mrope", "textattn"]
+    which = sys.argv[1:] or ["cfg3", "cfg3native", "cfg4", "cfg5", "mrope", "textattn", "cfg1", "latency"]
     _lib.lib()
     for w in which:
-        {"cfg3": lambda: cfg3(False), "cfg3native": lambda: cfg3(True), "cfg4": cfg4, "cfg5": cfg5, "mrope": mrope, "textattn": textattn}[w]()
+        {"cfg3": lambda: cfg3(False), "cfg3native": lambda: cfg3(True), "cfg4": cfg4, "cfg5": cfg5, "mrope": mrope, "textattn": textattn, "cfg1": cfg1, "latency": latency}[w]()
         torch.cuda.empty_cache()
