@@ -16,8 +16,8 @@
 //   warps 0..3  softmax, one thread per query row (lean step: packed f32x2 math, first-tile max as reference,
 //               step redone with a fresh max only when a row sum runs past 2^60 — see vf_attention.cu);
 //   warp 4      TMA loader: Q (4 swizzle atoms of 64 dims) once per item, K and V tiles through 2-stage rings;
-//   warp 5      MMA issuer: S(j+1) = Q K_{j+1}^T is issued BEFORE waiting for P(j), so it runs under the softmax of
-//               step j; then O += P(j) V_j. One thread's MMAs retire in order, which makes the S/P aliasing safe.
+//   warp 5      issuer of S(j+1) = Q K_{j+1}^T: runs one step ahead, under the softmax of step j (waits only for the PV
+//               that last read the target buffer); warp 6: issuer of O += P(j) V_j as soon as P(j) is stored.
 // Work item = (sample, query head, 128-row query tile), causal: key tiles 0 .. 2*tile+1 only; items are walked in
 // decreasing cost (last query tiles first), boustrophedon over the CTAs.
 #include "vf_common.cuh"
@@ -29,7 +29,7 @@ namespace vf {
 constexpr int GD = 256;                      // head dim
 constexpr int GKT = 64;                      // keys per tile
 constexpr int G_ATOMS = GD / 64;             // 128-byte swizzle atoms per row
-constexpr int G_THREADS = 192;
+constexpr int G_THREADS = 224;
 constexpr int G_STAGES = 2;
 constexpr int GQ_ATOM_BYTES = 128 * 128;     // 128 rows x 64 dims
 constexpr int GKV_ATOM_BYTES = GKT * 128;    // 64 keys x 64 dims
@@ -115,8 +115,8 @@ attention_gqa_kernel(const GqaParams p, const __grid_constant__ CUtensorMap tmQ,
   uint64_t* v_empty = v_full + G_STAGES;
   uint64_t* s_full = v_empty + G_STAGES;   // [2] per S buffer
   uint64_t* p_full = s_full + 2;           // [2]
-  uint64_t* pv_done = p_full + 2;          // [1] completes once per PV
-  uint64_t* o_full = pv_done + 1;          // [1]
+  uint64_t* pv_done = p_full + 2;          // [2] per S/P buffer: PV that read P from it has retired
+  uint64_t* o_full = pv_done + 2;          // [1]
   uint64_t* o_empty = o_full + 1;          // [1]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_empty + 1);
   const char* const WHO = "vf_attention_gqa";
@@ -140,7 +140,8 @@ attention_gqa_kernel(const GqaParams p, const __grid_constant__ CUtensorMap tmQ,
       mbar_init(&s_full[i], 1);
       mbar_init(&p_full[i], 4);
     }
-    mbar_init(pv_done, 1);
+    mbar_init(&pv_done[0], 1);
+    mbar_init(&pv_done[1], 1);
     mbar_init(o_full, 1);
     mbar_init(o_empty, 4);
     fence_barrier_init();
@@ -186,47 +187,52 @@ attention_gqa_kernel(const GqaParams p, const __grid_constant__ CUtensorMap tmQ,
       }
     }
   } else if (warp == 5) {
-    // -------------------------------------------------------------------- MMA issuer
+    // -------------------------------------------------------------------- issuer of S(j) = Q K_j^T
+    // Its own warp: issuing the 16 MMAs of one S takes longer than the four of a PV, and in one thread it would sit
+    // between P(j) becoming ready and PV(j) being issued. S(j) may overwrite its buffer once the PV that read P(j-2)
+    // from it has retired (pv_done of that buffer) — the two issuers are separate threads, so program order does not
+    // give that any more.
     constexpr uint32_t idesc_s = umma_idesc_bf16(128, GKT, 0, 0);
-    constexpr uint32_t idesc_o = umma_idesc_bf16(128, GD, 0, 1);   // N = 256: V is MN-major, four 64-dim atoms (LBO)
     const uint32_t q_addr = smem_u32(smem + GqaSmem::Q_OFF);
     const uint32_t k_addr = smem_u32(smem + GqaSmem::K_OFF);
-    const uint32_t v_addr = smem_u32(smem + GqaSmem::V_OFF);
-    int ks = 0, vs = 0;
-    uint32_t kph = 0, vph = 0, qph = 0, oeph = 0;
+    int ks = 0;
+    uint32_t kph = 0, qph = 0;
     unsigned g = 0;   // global key-step counter: S buffer = g & 1, barrier parity = (g >> 1) & 1
-    auto issue_s = [&](unsigned gs, int kstage) {
-      if (elect_one()) {
-        const uint32_t d = tmem_base + GT_S + (gs & 1) * 64;
-#pragma unroll
-        for (int kk = 0; kk < GD / 16; ++kk) {
-          const int a = kk >> 2, i = kk & 3;
-          umma_ss(d, umma_desc_sw128(q_addr + a * GQ_ATOM_BYTES) + 2 * i,
-                  umma_desc_sw128(k_addr + kstage * GKV_BYTES + a * GKV_ATOM_BYTES) + 2 * i, idesc_s, kk != 0);
-        }
-        umma_commit(&s_full[gs & 1]);
-        umma_commit(&k_empty[kstage]);
-      }
-      __syncwarp();
-    };
     int item;
     for (GqaIter it(p.n_items); it.next(item);) {
       const GqaItem w = gqa_decode(p, item);
       mbar_wait_or_trap(q_full, qph, WHO); qph ^= 1;
-      mbar_wait_or_trap(&k_full[ks], kph, WHO);
-      tc_fence_after();
-      issue_s(g, ks);
-      if (++ks == G_STAGES) { ks = 0; kph ^= 1; }
       for (int j = 0; j < w.n_kt; ++j, ++g) {
-        if (j + 1 < w.n_kt) {   // S(j+1) runs under the softmax of step j
-          mbar_wait_or_trap(&k_full[ks], kph, WHO);
-          tc_fence_after();
-          issue_s(g + 1, ks);
-          if (++ks == G_STAGES) { ks = 0; kph ^= 1; }
-        } else if (elect_one()) {
-          umma_commit(q_empty);   // every S of this item has been issued
+        mbar_wait_or_trap(&k_full[ks], kph, WHO);
+        if (g >= 2) mbar_wait_or_trap(&pv_done[g & 1], ((g >> 1) - 1) & 1, WHO);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t d = tmem_base + GT_S + (g & 1) * 64;
+#pragma unroll
+          for (int kk = 0; kk < GD / 16; ++kk) {
+            const int a = kk >> 2, i = kk & 3;
+            umma_ss(d, umma_desc_sw128(q_addr + a * GQ_ATOM_BYTES) + 2 * i,
+                    umma_desc_sw128(k_addr + ks * GKV_BYTES + a * GKV_ATOM_BYTES) + 2 * i, idesc_s, kk != 0);
+          }
+          umma_commit(&s_full[g & 1]);
+          umma_commit(&k_empty[ks]);
+          if (j + 1 == w.n_kt) umma_commit(q_empty);   // every S of this item has been issued
         }
         __syncwarp();
+        if (++ks == G_STAGES) { ks = 0; kph ^= 1; }
+      }
+    }
+  } else if (warp == 6) {
+    // -------------------------------------------------------------------- issuer of O += P(j) V_j
+    constexpr uint32_t idesc_o = umma_idesc_bf16(128, GD, 0, 1);   // N = 256: V is MN-major, four 64-dim atoms (LBO)
+    const uint32_t v_addr = smem_u32(smem + GqaSmem::V_OFF);
+    int vs = 0;
+    uint32_t vph = 0, oeph = 0;
+    unsigned g = 0;
+    int item;
+    for (GqaIter it(p.n_items); it.next(item);) {
+      const GqaItem w = gqa_decode(p, item);
+      for (int j = 0; j < w.n_kt; ++j, ++g) {
         mbar_wait_or_trap(&v_full[vs], vph, WHO);
         mbar_wait_or_trap(&p_full[g & 1], (g >> 1) & 1, WHO);
         if (j == 0) { mbar_wait_or_trap(o_empty, oeph ^ 1, WHO); oeph ^= 1; }
@@ -240,7 +246,7 @@ attention_gqa_kernel(const GqaParams p, const __grid_constant__ CUtensorMap tmQ,
                     j > 0 || k_ != 0);
           }
           umma_commit(&v_empty[vs]);
-          umma_commit(pv_done);
+          umma_commit(&pv_done[g & 1]);
           if (j + 1 == w.n_kt) umma_commit(o_full);
         }
         __syncwarp();
@@ -313,7 +319,7 @@ attention_gqa_kernel(const GqaParams p, const __grid_constant__ CUtensorMap tmQ,
         if (j == 0) m = row_max();               // key 0 is visible to every row, so m is finite
         float ssum = exp_store(m * p.scale_log2);
         if (j > 0 && __any_sync(0xffffffffu, !(ssum <= 0x1p60f))) {   // runaway exponent: redo with a fresh max
-          mbar_wait_or_trap(pv_done, (g - 1) & 1, WHO);                // O is stable once PV(previous step) retired
+          mbar_wait_or_trap(&pv_done[(g - 1) & 1], ((g - 1) >> 1) & 1, WHO);   // O is stable once PV(previous step) retired
           tc_fence_after();
           const float mx = row_max();
           const bool grow = mx > m;
