@@ -18,6 +18,11 @@
 //   warp 4      TMA loader: Q (4 swizzle atoms of 64 dims) once per item, K and V tiles through 2-stage rings;
 //   warp 5      issuer of S(j+1) = Q K_{j+1}^T: runs one step ahead, under the softmax of step j (waits only for the PV
 //               that last read the target buffer); warp 6: issuer of O += P(j) V_j as soon as P(j) is stored.
+// Measured and not kept (round 1, B=32 S=2832 with gate): eight softmax warps, two per lane quarter each owning 32 of a
+// tile's 64 key columns (1329 us vs 1230), and additionally four S buffers + a 3-stage K ring so that S can run three
+// steps ahead (1352 us). The step (~1850 cycles for 1024 cycles of ideal tensor work) is therefore not bound by the
+// softmax or by the S/PV dependency; the QK^T MMAs at N = 64 read 6 KB of shared memory per 32-cycle MMA (A 128x16 +
+// B 64x16), above the 128 B/clk the SM delivers — the fix is a wider N per MMA (CTA pairs sharing the K tile).
 // Work item = (sample, query head, 128-row query tile), causal: key tiles 0 .. 2*tile+1 only; items are walked in
 // decreasing cost (last query tiles first), boustrophedon over the CTAs.
 #include "vf_common.cuh"
