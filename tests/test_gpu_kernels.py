@@ -438,3 +438,48 @@ def test_mrope_strided_in_place_equals_contiguous(L, golden_rope):
     assert torch.equal(got.cpu(), ref.cpu())
     untouched = d.cpu()[:, 64:].view(B, S, H, 512)[..., 256:]
     assert torch.equal(untouched, buf[:, 64:].view(B, S, H, 512)[..., 256:]) and torch.equal(d.cpu()[:, :64], buf[:, :64])
+
+
+def test_position_ids_and_scatter_randomised_vs_oracle(L):
+    """Bit-exact integer work on 40 random early-fusion batches: ragged placeholder runs, several feeds of different
+    (t, h, w), samples without images, starved feeds, explicit masks — kernel == numpy oracle, every element."""
+    rng = np.random.default_rng(2024)
+    tok = 248056
+    for case in range(40):
+        b = int(rng.integers(1, 6))
+        n_feeds = int(rng.integers(1, 4))
+        feeds = [[int(rng.integers(1, 4)), 2 * int(rng.integers(1, 5)), 2 * int(rng.integers(1, 5))] for _ in range(n_feeds)]
+        need = [f[0] * (f[1] // 2) * (f[2] // 2) for f in feeds]
+        seq = int(sum(need) + rng.integers(n_feeds + 2, 60))
+        ids = rng.integers(0, 1000, size=(b, seq)).astype(np.int64)
+        for s in range(b):
+            mode = rng.integers(0, 4)          # 0: all feeds, 1: no image, 2: starved last feed, 3: all feeds, shuffled gaps
+            if mode == 1:
+                continue
+            pos = int(rng.integers(0, 3))
+            for i, n in enumerate(need):
+                n_put = n if not (mode == 2 and i == n_feeds - 1) else max(0, n - int(rng.integers(1, n + 1)))
+                if pos + n_put > seq:
+                    break
+                ids[s, pos:pos + n_put] = tok
+                pos += n_put + int(rng.integers(1, 4))
+        use_mask = case % 3 == 0
+        mask = (ids == tok) if use_mask else None
+        exp = FO.mrope_position_ids(ids, feeds, mask, tok, 2)
+        got = L.mrope_position_ids(dev(torch.from_numpy(ids)), None if mask is None else dev(torch.from_numpy(mask)), tok,
+                                   torch.tensor(feeds), 2)
+        assert np.array_equal(got.cpu().numpy(), exp), f"case {case}: feeds={feeds} b={b} seq={seq}"
+        # gather/scatter placement on the same ids
+        D, V = 64, 1000
+        table = bf(rnd(V, D, seed=100 + case))
+        n_ph = int((ids == tok).sum())
+        vision = bf(rnd(max(n_ph, 1) + 3, D, seed=200 + case))
+        row_map, count, _ = L.fuse_scan(dev(torch.from_numpy(ids)), None, tok)
+        assert int(count.item()) == n_ph
+        assert np.array_equal(row_map.cpu().numpy(), FO.scatter_row_map(ids, None, tok).reshape(-1))
+        out = torch.empty((b, seq, D), dtype=torch.bfloat16, device="cuda")
+        L.embed_gather_scatter(dev(torch.from_numpy(ids)), dev(table), dev(vision), row_map, out)
+        flat = torch.from_numpy(ids).view(-1)
+        got_e = out.cpu().view(-1, D)
+        assert torch.equal(got_e[flat != tok], table[flat[flat != tok]])
+        assert torch.equal(got_e[flat == tok], vision[:n_ph])
