@@ -4,6 +4,7 @@
 
 #include <atomic>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <stdio.h>
 
 namespace vf {
@@ -26,6 +27,17 @@ int check_cuda(cudaError_t e, const char* what) {
 }
 
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    // opt-in (VF_PDL=1): measured neutral for throughput at batch 64 (12.9-13.1 ms per step either way, inside the
+    // power-cap noise) and worth 2-7 % for CUDA-graph latency at batch 1-4 (1.069 -> 0.998 ms at batch 1)
+    const char* e = getenv("VF_PDL");
+    on = (e && e[0] == '1') ? 1 : 0;
+  }
+  return on != 0;
+}
 
 int device_sm_count() {
   static int sms = -1;

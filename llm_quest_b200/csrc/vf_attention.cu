@@ -197,6 +197,8 @@ attention_kernel(const AttnParams p, const __grid_constant__ CUtensorMap tmQ,
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                 // the QKV projection's output is complete and visible from here on
+  pdl_launch_dependents();
 
   if (warp >= NQ * 4) {
     // loader / MMA / idle warps: hand registers to the softmax warpgroups. Budget: the CTA owns
@@ -635,7 +637,8 @@ extern "C" int vf_attention_fwd(const void* qkv, void* out, int32_t B, int32_t S
     configured[flags] = true;
   }
   const int grid = p.n_items < sms ? p.n_items : sms;
-  kerns[flags]<<<grid, ATT_THREADS, AttnSmem::TOTAL, static_cast<cudaStream_t>(stream)>>>(p, tmQ, tmKV);
+  VF_CUDA(launch_pdl(kerns[flags], dim3(grid), dim3(ATT_THREADS), AttnSmem::TOTAL, static_cast<cudaStream_t>(stream), 1, p,
+                     tmQ, tmKV));
   count_launch();
   VF_CUDA(cudaGetLastError());
   return VF_OK;

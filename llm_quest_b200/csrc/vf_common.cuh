@@ -49,8 +49,46 @@ int encode_tmap(CUtensorMap* out, CUtensorMapDataType dt, uint32_t rank, const v
 
 int device_sm_count();
 void count_launch();  // bumps the counter behind vf_launch_count()
+bool pdl_enabled();   // programmatic dependent launch between consecutive libvfuse kernels (opt-in: VF_PDL=1)
 
 #ifdef __CUDACC__
+// ----------------------------------------------------------------------------------------------
+// Programmatic dependent launch: a kernel launched with launch_pdl() may become resident while its predecessor in
+// the stream is still draining; its prologue (barrier init, TMEM allocation, tensor-map prefetch) then overlaps the
+// predecessor's tail and the launch latency. It must call pdl_wait() before it touches anything the predecessor
+// wrote (and before it writes anything the predecessor may still read); pdl_launch_dependents() lets ITS successor
+// start launching. Without the launch attribute both are no-ops.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              int cluster_x, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (cluster_x > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = cluster_x;
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (pdl_enabled()) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ----------------------------------------------------------------------------------------------
 // generic device helpers
 // ----------------------------------------------------------------------------------------------

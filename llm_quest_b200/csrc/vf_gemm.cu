@@ -158,6 +158,8 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
   if constexpr (CG == 2) cluster_sync_all();   // barrier inits + TMEM of both CTAs visible to the pair
   else __syncthreads();
   tc_fence_after();
+  pdl_wait();                 // everything above overlapped the previous kernel's tail; its results are visible now
+  pdl_launch_dependents();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
@@ -553,19 +555,7 @@ static int launch_gemm(const GemmParams& p, const CUtensorMap& tmA, const CUtens
   const int tiles = ((p.num_m_blk + CG - 1) / CG) * p.num_n_blk;
   const int slots = sms / CG;                       // persistent: one CTA (pair) per SM (pair)
   const int grid = (tiles < slots ? tiles : slots) * CG;
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(EpiCfg<EPI>::THREADS);
-  cfg.dynamicSmemBytes = L::TOTAL;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CG;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  VF_CUDA(cudaLaunchKernelEx(&cfg, kfn, p, tmA, tmB));
+  VF_CUDA(launch_pdl(kfn, dim3(grid), dim3(EpiCfg<EPI>::THREADS), L::TOTAL, stream, CG, p, tmA, tmB));
   count_launch();
   VF_CUDA(cudaGetLastError());
   return VF_OK;

@@ -48,6 +48,8 @@ layernorm_kernel(const TIn* __restrict__ x, long long ldx, const float* __restri
   constexpr int D = NV * 128;
   const int lane = threadIdx.x & 31;
   const long long row = static_cast<long long>(blockIdx.x) * LN_WARPS + (threadIdx.x >> 5);
+  pdl_wait();
+  pdl_launch_dependents();
   if (row >= rows) return;
 
   float v[NV][4];
@@ -105,8 +107,8 @@ static int launch_ln(const void* x, long long ldx, const float* w, const float* 
   TOut* o = static_cast<TOut*>(out);
 #define VF_LN_CASE(NV)                                                                            \
   case NV:                                                                                        \
-    layernorm_kernel<TIn, TOut, NV><<<grid, LN_WARPS * 32, 0, s>>>(xi, ldx, w, b, o, rows, eps,    \
-                                                                  variant, merge, nh, nw);        \
+    VF_CUDA(launch_pdl(layernorm_kernel<TIn, TOut, NV>, dim3(grid), dim3(LN_WARPS * 32), 0, s, 1, xi, \
+                       static_cast<long long>(ldx), w, b, o, static_cast<long long>(rows), eps, variant, merge, nh, nw)); \
     break;
   switch (D / 128) {
     VF_LN_CASE(1) VF_LN_CASE(2) VF_LN_CASE(3) VF_LN_CASE(4) VF_LN_CASE(6) VF_LN_CASE(8)
