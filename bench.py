@@ -187,27 +187,50 @@ def run_ours(args):
     dev_px = host_px.to(dev, non_blocking=True)
     n_out = S // 4
 
+    # N > 1: the all-gather is FUSED into the tower's last GEMM — its epilogue stores this rank's rows into every
+    # rank's gathered buffer over NVLink peer memory (parallel.FusedAllGather), followed by a signal-pad barrier; no
+    # NCCL kernel competes with the persistent kernels for SMs. If peer memory cannot be set up the NCCL all-gather
+    # on a side stream is used instead (recorded in config.parallelism).
+    fused, overlap, gather_kind = None, None, "none"
+    if world > 1:
+        try:
+            fused = parallel.FusedAllGather(rows_local=B * n_out, cols=1024)
+            gather_kind = ("all-gather fused into the last GEMM (" + ("NVSwitch multicast stores" if fused.multicast_ptr else "NVLink peer stores")
+                           + " + signal barrier)")
+        except Exception as e:  # noqa: BLE001
+            print(f"[bench] fused all-gather unavailable ({type(e).__name__}: {e}); using NCCL", file=sys.stderr, flush=True)
+            overlap = parallel.OverlappedAllGather(dev)
+            gather_kind = "NCCL all-gather of merged embeddings on a side stream"
+
     def step_resident():
+        if fused is not None:
+            return model(dev_px, gather=fused)
         out = model(dev_px)
-        if world > 1:
-            out = parallel.all_gather_cat(out.to(torch.bfloat16), 0)
+        if overlap is not None:
+            out, _ = overlap.submit(out.to(torch.bfloat16))
         return out
 
     from llm_quest_b200.pipeline import StreamedEncoder
 
-    # N > 1: the merged embeddings are all-gathered ON THE DEVICE (where the downstream LLM consumes them) inside the
-    # step; the host read of the step's result is each rank's own shard (every row of the job's output crosses PCIe
-    # once). Downloading the whole gathered batch on every rank (world x 25 MB per step and rank) saturated host
-    # memory at 8 ranks: 18.6 k img/s end to end against 38.6 k device-resident.
+    # End to end at N > 1 the gathered batch stays in HBM (where the downstream LLM consumes it); the host read of the
+    # step's result is each rank's own shard (every row of the job's output crosses PCIe once). Downloading the whole
+    # gathered batch on every rank saturated host memory at 8 ranks: 18.6 k img/s against 38.6 k device-resident.
     gathered = [None]
 
     def gather_keep_local(o):
         local = o.to(torch.bfloat16)
-        gathered[0] = parallel.all_gather_cat(local, 0)
+        gathered[0] = overlap.submit(local)
         return local
 
-    gather = gather_keep_local if world > 1 else None
-    enc = StreamedEncoder(model, depth=2, device=dev, post_fn=gather)
+    def fused_model(x):
+        full = model(x, gather=fused)            # [world*B, n_out, 1024] bf16 on every rank
+        gathered[0] = full
+        return full[rank * B:(rank + 1) * B]
+
+    if fused is not None:
+        enc = StreamedEncoder(fused_model, depth=2, device=dev)
+    else:
+        enc = StreamedEncoder(model, depth=2, device=dev, post_fn=gather_keep_local if overlap is not None else None)
     sink = [0.0]
 
     def run_e2e(steps):
@@ -293,7 +316,7 @@ def run_ours(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": f"cfg2: Qwen3.5 Qwen3-ViT tower + spatial-merge adapter, {px}x{px}, T=2, batch {B} per GPU",
                        "global_batch": world * B, "tokens_per_image": S, "l2_policy": "inputs_larger_than_l2 (154 MB pixels + 1.3 GB activations per step)",
-                       "parallelism": f"sample-sharded x{world}" + (" + NCCL all-gather of merged embeddings" if world > 1 else "")},
+                       "parallelism": f"sample-sharded x{world}" + (f" + {gather_kind}" if world > 1 else "")},
             "step_tflops": round(step_tflops, 1), "step_frac_of_peak": round(step_tflops / peaks["bf16_tflops"], 3),
             "roofline": {"bound": "tensor", "kernel": "vf::gemm_kernel<EPI,BN> (tcgen05, all epilogues; incl. patch-embed gather GEMM)",
                          "achieved": round(achieved, 1), "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",

@@ -84,6 +84,12 @@ typedef struct {
   int32_t rope_cols;       /* columns [0, rope_cols) are rotated (q and k); multiple of 64 */
   /* VF_EPI_SCATTER_BF16 */
   const int32_t* dst_rows; /* [M] destination row or -1 */
+  /* Fused all-gather (VF_EPI_BIAS_BF16 / VF_EPI_BIAS_F32, n_peers > 0): every output element is stored to the same
+   * (row, column) of EACH of the n_peers buffers instead of `out` — peer-mapped device memory of the other GPUs of
+   * the box (NVLink P2P) plus this GPU's own copy, each pointer already offset to this rank's first row. Replaces
+   * "GEMM, then ncclAllGather of its output" for the sample-sharded path. `out` is ignored. */
+  int32_t n_peers;         /* 0 = store to `out` only */
+  void* peer_out[8];
 } vf_epilogue;
 
 int vf_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, int32_t M, int32_t N,

@@ -53,6 +53,8 @@ class vf_epilogue(C.Structure):
         ("rope_period", C.c_int32),
         ("rope_cols", C.c_int32),
         ("dst_rows", C.c_void_p),
+        ("n_peers", C.c_int32),
+        ("peer_out", C.c_void_p * 8),
     ]
 
 
@@ -190,8 +192,11 @@ _EPI_NAMES = {0: "bias_bf16", 1: "bias_f32", 2: "bias_res_f32", 3: "gelu_tanh_bf
 # ------------------------------------------------------------------------------------------------
 # tensor-level wrappers
 # ------------------------------------------------------------------------------------------------
-def gemm(a, w, mode, out, bias=None, res=None, rope=None, dst_rows=None, grp_rows=0, grp_stride=0, row_off=0):
-    """out = epilogue(a @ w.T). a [M,K] bf16 (row stride free), w [N,K] bf16, see vf_epilogue_mode."""
+def gemm(a, w, mode, out, bias=None, res=None, rope=None, dst_rows=None, grp_rows=0, grp_stride=0, row_off=0,
+         peer_ptrs=None):
+    """out = epilogue(a @ w.T). a [M,K] bf16 (row stride free), w [N,K] bf16, see vf_epilogue_mode.
+    peer_ptrs: device pointers (ints) of up to 8 destination buffers shaped like `out` (fused all-gather: the rows
+    are stored to every one of them, `out` only provides dtype and row pitch)."""
     _require_cuda(a, w, out, bias, res, dst_rows)
     assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and a.dim() == 2 and w.dim() == 2
     assert a.stride(1) == 1 and w.stride(1) == 1 and out.stride(-1) == 1
@@ -213,6 +218,11 @@ def gemm(a, w, mode, out, bias=None, res=None, rope=None, dst_rows=None, grp_row
         assert cos_h.dtype == torch.float32 and cos_h.shape[-1] == 32 and cos_h.is_contiguous()
         ep.rope_cos, ep.rope_sin, ep.rope_period, ep.rope_cols = cos_h.data_ptr(), sin_h.data_ptr(), period, cols
     ep.dst_rows = _p(dst_rows)
+    if peer_ptrs:
+        assert len(peer_ptrs) <= 8
+        ep.n_peers = len(peer_ptrs)
+        for i, ptr in enumerate(peer_ptrs):
+            ep.peer_out[i] = int(ptr)
     if bias is not None:
         assert bias.dtype == torch.float32 and bias.is_contiguous() and bias.numel() == N
     with _timed("gemm_" + _EPI_NAMES.get(mode, str(mode)), flops=2.0 * M * N * K):

@@ -55,6 +55,8 @@ struct GemmParams {
   int rope_cols;
   const int* dst_rows;
   int vec_ok;          // out (and res) rows are 16-byte aligned: 128-bit stores allowed
+  int n_peers;         // > 0: fused all-gather, every element goes to peer[0..n_peers) (NVLink peer memory) instead of out
+  char* peer[8];
   // patch-embedding mode
   int patch;
   int PW, PH;          // tile rectangle in patches (PW*PH == 128)
@@ -484,6 +486,18 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
                   for (int e = 0; e < 4; ++e) v[e] = gelu_erf_f(v[e]);
                 }
                 if (!decltype(guarded)::value || orow[i] >= 0) {
+                  if constexpr (EPI == VF_EPI_BIAS_BF16 || EPI == VF_EPI_BIAS_F32) {
+                    if (p.n_peers > 0) {   // fused all-gather: the same element to every GPU's copy of the gathered buffer
+                      const long long off = (obase[i] - reinterpret_cast<char*>(p.out)) + (long long)cc * ESZ;
+                      for (int r = 0; r < p.n_peers; ++r) {
+                        if constexpr (OUT_F32)
+                          *reinterpret_cast<float4*>(p.peer[r] + off) = make_float4(v[0], v[1], v[2], v[3]);
+                        else
+                          *reinterpret_cast<uint2*>(p.peer[r] + off) = make_uint2(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]));
+                      }
+                      continue;
+                    }
+                  }
                   if constexpr (OUT_F32)
                     *reinterpret_cast<float4*>(obase[i] + cc * 4) = make_float4(v[0], v[1], v[2], v[3]);
                   else
@@ -632,6 +646,19 @@ extern "C" int vf_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t l
   p.rope_period = ep->rope_period; p.rope_cols = ep->rope_cols;
   p.dst_rows = ep->dst_rows;
   p.vec_ok = vec_ok ? 1 : 0;
+  p.n_peers = 0;
+  if (ep->n_peers > 0) {
+    VF_REQUIRE(ep->n_peers <= 8, VF_ERR_ARG, "vf_gemm_bf16: at most 8 peer buffers");
+    VF_REQUIRE(ep->mode == VF_EPI_BIAS_BF16 || ep->mode == VF_EPI_BIAS_F32, VF_ERR_ARG,
+               "vf_gemm_bf16: the fused all-gather needs the bias_bf16 or bias_f32 epilogue");
+    VF_REQUIRE(vec_ok && (N & 3) == 0, VF_ERR_ALIGN, "vf_gemm_bf16: the fused all-gather needs aligned rows and N %% 4 == 0");
+    for (int i = 0; i < ep->n_peers; ++i) {
+      VF_REQUIRE(ep->peer_out[i] && (reinterpret_cast<uintptr_t>(ep->peer_out[i]) & 15) == 0, VF_ERR_ALIGN,
+                 "vf_gemm_bf16: peer buffer %d is null or not 16-byte aligned", i);
+      p.peer[i] = reinterpret_cast<char*>(ep->peer_out[i]);
+    }
+    p.n_peers = ep->n_peers;
+  }
 
   // CTA pairs for every 256-wide problem with at least one full pair of row blocks per SM pair
   // (VF_GEMM_CG=1 forces the single-CTA kernel: development A/B switch)

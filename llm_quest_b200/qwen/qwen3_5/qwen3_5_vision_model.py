@@ -253,9 +253,10 @@ class ViTMergeAdapter(nn.Module):
         self.lin2 = nn.Linear(self.merged_size, llm_d_in)
         self._packed = _Packed()
 
-    def merge_project(self, x2d, out=None, dst_rows=None):
+    def merge_project(self, x2d, out=None, dst_rows=None, peer_ptrs=None):
         """x2d fp32/bf16 [B*S, D] -> [B*S/m^2, llm_d_in]. With `dst_rows` (int32 per merged row) the
-        last GEMM scatters bf16 rows straight into `out` (the fused text sequence)."""
+        last GEMM scatters bf16 rows straight into `out` (the fused text sequence); with `peer_ptrs` it stores
+        them into the gathered buffer of every rank (fused all-gather, see parallel.FusedAllGather)."""
         c = self._packed
         nw_, nb_ = _f32(c, "nw", self.norm.weight), _f32(c, "nb", self.norm.bias)
         w1, b1 = _w_bf16(c, "w1", self.lin1.weight), _f32(c, "b1", self.lin1.bias)
@@ -273,7 +274,7 @@ class ViTMergeAdapter(nn.Module):
         if out is None:
             out = torch.empty((rows // mm, w2.shape[0]), dtype=torch.float32, device=x2d.device)
         mode = VF_EPI_BIAS_F32 if out.dtype == torch.float32 else VF_EPI_BIAS_BF16
-        _lib.gemm(g, w2, mode, out, bias=b2)
+        _lib.gemm(g, w2, mode, out, bias=b2, peer_ptrs=peer_ptrs)
         return out
 
     def forward(self, x):
@@ -357,14 +358,21 @@ class Qwen3_5VisionModel(nn.Module):
             block.run_(x2d, B, S, rope, work)
         return x2d, B, S
 
-    def forward(self, x, out=None, dst_rows=None):
+    def forward(self, x, out=None, dst_rows=None, gather=None):
         """x: [B, C, T, H, W] pixels. Returns [B, num_merged_patches, llm_d_in].
 
         `out`/`dst_rows` (library extension, used by Qwen3_5VLM): scatter the merged rows as bf16
         directly into the fused text-embedding buffer instead of returning them.
+        `gather` (library extension, sample-sharded multi-GPU runs): a parallel.FusedAllGather — the last GEMM stores
+        this rank's rows into every rank's gathered buffer; returns [world*B, num_merged_patches, llm_d_in] bf16.
         """
         _forward_only_guard(self)
         x2d, B, S = self.encode_hidden(x)
+        if gather is not None:
+            slot = gather.next_slot()
+            self.merge_adapter.merge_project(x2d, out=gather.local_rows(slot), peer_ptrs=gather.peer_ptrs(slot))
+            gather.barrier()
+            return gather.gathered(slot).view(gather.world * B, -1, gather.cols)
         if dst_rows is not None:
             return self.merge_adapter.merge_project(x2d, out=out, dst_rows=dst_rows)
         merged = self.merge_adapter.merge_project(x2d)

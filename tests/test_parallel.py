@@ -7,6 +7,7 @@ bounds, dim-0 gather of embeddings, dim-1 gather of the [3, b, seq] position ids
 """
 
 import os
+from pathlib import Path
 import socket
 
 import numpy as np
@@ -85,3 +86,20 @@ def test_streamed_encoder_rejects_cpu_model():
 
     with pytest.raises(RuntimeError):
         StreamedEncoder(torch.nn.Linear(2, 2))
+
+
+@pytest.mark.gpu
+def test_fused_all_gather_two_gpus():
+    """The all-gather fused into the last GEMM's epilogue (peer stores over NVLink) == NCCL all-gather, bit for bit."""
+    import subprocess
+    import sys
+
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs on one box")
+    root = Path(__file__).resolve().parent.parent
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29577", str(root / "tests" / "mp_fused_gather.py")],
+                       capture_output=True, text=True, timeout=600)
+    assert "FUSED_GATHER_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
