@@ -147,7 +147,9 @@ __device__ __forceinline__ int pair_bh(const AttnParams& p, int item, int m) {
 // 2459 us at S=6272), a one-time 250-800 cycle stagger of the four chains (2620-2930 vs 2340 us), polling with
 // mbarrier.test_wait instead of the suspending try_wait (2522 vs 2328 us), skipping the exponentials of masked
 // 16-key chunks and running the ragged last query tile on one lane quarter only (no change at S=784: a key
-// step there is bound by the chain's serial latency, not by the amount of exponentials).
+// step there is bound by the chain's serial latency, not by the amount of exponentials), and evaluating every 4th /
+// 3rd / 2nd pair of exponentials on the FMA pipe (Cody-Waite split + degree-3 minimax polynomial, packed f32x2:
+// 2414 / 2501 / 2813 us against 2296 at S=6272 — the softmax warps are short of issue slots, not of MUFU cycles).
 
 template <int FLAGS>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
