@@ -483,3 +483,22 @@ def test_position_ids_and_scatter_randomised_vs_oracle(L):
         got_e = out.cpu().view(-1, D)
         assert torch.equal(got_e[flat != tok], table[flat[flat != tok]])
         assert torch.equal(got_e[flat == tok], vision[:n_ph])
+
+
+def test_error_paths_on_device(L):
+    """The C ABI reports misuse instead of computing something else: misaligned rows, unsupported head_dim, wrong
+    epilogue for the fused all-gather, CPU tensors."""
+    a, w = dev(bf(rnd(64, 128, seed=1))), dev(bf(rnd(96, 128, seed=2)))
+    out = torch.empty((64, 96), dtype=torch.bfloat16, device="cuda")
+    with pytest.raises(L.VFuseError, match="fused all-gather"):
+        L.gemm(a, w, L.VF_EPI_GELU_TANH_BF16, out, peer_ptrs=[out.data_ptr()])
+    a_odd = dev(bf(rnd(64, 132, seed=4)))[:, :128]                         # row pitch 132 elements: not 16-byte aligned rows
+    with pytest.raises(L.VFuseError, match="multiples of 8"):
+        L.gemm(a_odd, w, L.VF_EPI_BIAS_BF16, out)
+    q = dev(bf(rnd(64, 2 * 128, seed=3)))
+    with pytest.raises(L.VFuseError, match="head_dim"):
+        L.lib()  # keep the library loaded
+        L.check(L.lib().vf_attention_gqa_fwd(q.data_ptr(), 256, 0, 128, q.data_ptr(), 256, q.data_ptr(), 256, out.data_ptr(), 96,
+                                             None, 0, 0, 0, 1, 64, 2, 2, 128, 0.1, 1, None), "vf_attention_gqa_fwd")
+    with pytest.raises(L.VFuseError, match="CPU tensor"):
+        L.gemm(a.cpu(), w, L.VF_EPI_BIAS_BF16, out)
