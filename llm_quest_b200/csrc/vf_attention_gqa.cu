@@ -11,18 +11,17 @@
 // At head_dim 256 the balance is the opposite of the vision kernel (vf_attention.cu): a 128 x 64 score tile costs
 // 1024 tensor cycles (QK^T over K=256 + PV over N=256) against 512 MUFU cycles, so ONE chain per CTA is enough if
 // the tensor core never waits for the softmax:
-//   TMEM (384 of 512 columns): S double-buffered at [0,64) / [64,128); P(j) overwrites S(j) in its buffer;
-//                              O at [128,384).
+//   TMEM (all 512 columns): S double-buffered at [0,64) / [64,128), P(j) overwrites S(j) in its buffer; Q (copied
+//                           from shared memory once per item, tcgen05.cp) at [128,256); O at [256,512).
 //   warps 0..3  softmax, one thread per query row (lean step: packed f32x2 math, first-tile max as reference,
 //               step redone with a fresh max only when a row sum runs past 2^60 — see vf_attention.cu);
 //   warp 4      TMA loader: Q (4 swizzle atoms of 64 dims) once per item, K and V tiles through 2-stage rings;
 //   warp 5      issuer of S(j+1) = Q K_{j+1}^T: runs one step ahead, under the softmax of step j (waits only for the PV
 //               that last read the target buffer); warp 6: issuer of O += P(j) V_j as soon as P(j) is stored.
-// Measured and not kept (round 1, B=32 S=2832 with gate): eight softmax warps, two per lane quarter each owning 32 of a
-// tile's 64 key columns (1329 us vs 1230), and additionally four S buffers + a 3-stage K ring so that S can run three
-// steps ahead (1352 us). The step (~1850 cycles for 1024 cycles of ideal tensor work) is therefore not bound by the
-// softmax or by the S/PV dependency; the QK^T MMAs at N = 64 read 6 KB of shared memory per 32-cycle MMA (A 128x16 +
-// B 64x16), above the 128 B/clk the SM delivers — the fix is a wider N per MMA (CTA pairs sharing the K tile).
+// Measured and not kept (round 1, B=32 S=2832 with gate, before Q moved to TMEM): eight softmax warps, two per lane
+// quarter each owning 32 of a tile's 64 key columns (1329 us vs 1230), and additionally four S buffers + a 3-stage K
+// ring so that S can run three steps ahead (1352 us): the step was bound neither by the softmax nor by the S/PV
+// dependency but by the shared-memory reads of the N = 64 QK^T MMAs (see the S issuer).
 // Work item = (sample, query head, 128-row query tile), causal: key tiles 0 .. 2*tile+1 only; items are walked in
 // decreasing cost (last query tiles first), boustrophedon over the CTAs.
 #include "vf_common.cuh"
@@ -40,7 +39,7 @@ constexpr int GQ_ATOM_BYTES = 128 * 128;     // 128 rows x 64 dims
 constexpr int GKV_ATOM_BYTES = GKT * 128;    // 64 keys x 64 dims
 constexpr int GQ_BYTES = G_ATOMS * GQ_ATOM_BYTES;     // 64 KB
 constexpr int GKV_BYTES = G_ATOMS * GKV_ATOM_BYTES;   // 32 KB
-constexpr int GT_S = 0, GT_O = 128;          // TMEM columns
+constexpr int GT_S = 0, GT_Q = 128, GT_O = 256;   // TMEM columns: S/P 2 x 64, Q 128 (bf16 pairs), O 256
 
 struct GqaParams {
   int B, S, Hq, Hkv;
@@ -207,6 +206,22 @@ attention_gqa_kernel(const GqaParams p, const __grid_constant__ CUtensorMap tmQ,
     for (GqaIter it(p.n_items); it.next(item);) {
       const GqaItem w = gqa_decode(p, item);
       mbar_wait_or_trap(q_full, qph, WHO); qph ^= 1;
+      tc_fence_after();
+      if (elect_one()) {
+        // Q: shared memory -> tensor memory once per item (16 copies of 128 rows x 16 dims). As an operand read from
+        // TMEM it costs the QK^T MMAs no shared-memory bandwidth: with Q in smem an N = 64 MMA read 6 KB per 32 cycles
+        // of math (A 128x16 + B 64x16), above the 128 B/clk an SM delivers. tcgen05.cp and tcgen05.mma of one thread
+        // execute in issue order, so the copies wait for the previous item's last S and this item's S wait for them.
+#pragma unroll
+        for (int kk = 0; kk < GD / 16; ++kk) {
+          const int a = kk >> 2, i = kk & 3;
+          asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(tmem_base + GT_Q + kk * 8),
+                       "l"(umma_desc_sw128(q_addr + a * GQ_ATOM_BYTES) + 2 * i)
+                       : "memory");
+        }
+        umma_commit(q_empty);   // the Q tile in shared memory is free once the copies have retired
+      }
+      __syncwarp();
       for (int j = 0; j < w.n_kt; ++j, ++g) {
         mbar_wait_or_trap(&k_full[ks], kph, WHO);
         if (g >= 2) mbar_wait_or_trap(&pv_done[g & 1], ((g >> 1) - 1) & 1, WHO);
@@ -216,12 +231,11 @@ attention_gqa_kernel(const GqaParams p, const __grid_constant__ CUtensorMap tmQ,
 #pragma unroll
           for (int kk = 0; kk < GD / 16; ++kk) {
             const int a = kk >> 2, i = kk & 3;
-            umma_ss(d, umma_desc_sw128(q_addr + a * GQ_ATOM_BYTES) + 2 * i,
+            umma_ts(d, tmem_base + GT_Q + kk * 8,
                     umma_desc_sw128(k_addr + ks * GKV_BYTES + a * GKV_ATOM_BYTES) + 2 * i, idesc_s, kk != 0);
           }
           umma_commit(&s_full[g & 1]);
           umma_commit(&k_empty[ks]);
-          if (j + 1 == w.n_kt) umma_commit(q_empty);   // every S of this item has been issued
         }
         __syncwarp();
         if (++ks == G_STAGES) { ks = 0; kph ^= 1; }
