@@ -6,16 +6,18 @@
 // at column offsets h*64, H*64+h*64, 2*H*64+h*64), and the context is written token-major
 // [B*S, H*64] — no head-major copy exists anywhere.
 //
-// At head_dim 64 this kernel is bound by the exponential unit (16 ex2/clk/SM), not by the tensor
-// pipe: one 128x64 score tile costs 256 MMA cycles (QK^T + PV) but 512 MUFU cycles. The design goal is
-// therefore to keep every SM sub-partition's MUFU busy, which needs many independent softmax chains:
+// At head_dim 64 the tensor pipe is NOT what bounds this kernel: one 128x64 score tile costs 256 MMA cycles (QK^T +
+// PV) but 512 MUFU cycles (16 ex2/clk/SM) and about as many issue cycles of the softmax warps (the FMA-pipe
+// polynomial exponential made it slower: issue slots are the scarcer of the two). The design goal is therefore to keep
+// every SM sub-partition busy with softmax work, which needs many independent chains:
 //
 //   one persistent CTA per SM; a work item is (sample b, head h, block of 512 queries) = FOUR
-//   128-row query tiles that share every 64-key K/V tile:
-//     warps 0..15   four softmax warpgroups (one per query tile), one thread per query row:
-//                   rowmax / exp2 / rowsum / P->TMEM / lazy O rescale / final O/l store
-//     warp 16       TMA loader: Q0..Q3 once per item; K and V tiles through two 4-stage rings
-//     warps 17,18   tcgen05.mma issuers (tiles {0,1} and {2,3}):
+//   128-row query tiles ("chains") that share every 64-key K/V tile:
+//     warps 0..15   four softmax warpgroups (one per query tile), one thread per query row: first-tile row max,
+//                   packed-f32x2 scale/exp2/row sum, P->TMEM, redo of a step with a fresh max + O rescale only when
+//                   its row sum runs past 2^60, final O/l store
+//     warp 16       TMA loader: Q0..Q3 once per item (double-buffered); K and V tiles through two 4-stage rings
+//     warps 17,18   tcgen05.mma issuers (tiles {0,1} and {2,3}), each walking its two tiles as independent chains:
 //                                        S_t = Q_t K_j^T  (SS, M=128, N=64,  K=64)
 //                                        O_t += P_t V_j   (TS: P_t bf16 in TMEM; V MN-major smem)
 //                   Measured: one issuer needs ~380 cycles to issue the 8 small MMAs of a tile-step,
@@ -25,19 +27,19 @@
 //   TMEM (512 cols): S_t at [64t, 64t+64), P_t aliases the first 32 columns of S_t (64 bf16),
 //                    O_t at [256+64t, 256+64t+64).
 //   Each softmax warp sits on one SM sub-partition together with the three warps that own the same
-//   lane quarter of the other tiles, so while one waits on its MMAs the others keep the MUFU fed.
-//   The MMA warp issues S_t(j+1) right behind PV_t(j); tcgen05.mma instructions of one thread retire
+//   lane quarter of the other tiles, so while one waits on its MMAs the others keep the sub-partition fed.
+//   A walker issues S_t(j+1) right behind PV_t(j); tcgen05.mma instructions of one thread retire
 //   in order, which is what makes the S/P aliasing and the in-place O rescale race-free.
+//   S <= 256 (pair mode): an item is a PAIR of (sample, head); chains 0,1 serve the first, 2,3 the second, each
+//   member with its own two-stage K/V ring.
 //
 //   Tried and measured slower on B200 (round 1): THREE chains with P in its own TMEM columns so
 //   that S_t(j+1) is computed while S_t(j) is exponentiated (one issuer warp per tile and product, exponentials
 //   kept in registers until PV_t(j-1) retires): 2.96 ms vs 2.23 ms at S=6272 — a chain's step is bound by the
 //   softmax warp's own ~2500-cycle serial path and by the issue cost of the small MMAs (~60 cycles per
 //   tcgen05.mma, ~100-200 per barrier operation), not by the QK^T round trip, so four chains beat three.
-//   Also: P in shared memory with S_t(j+1)
-//   issued as soon as S_t(j) is in registers (no MMA round trip on the softmax chain: 3.57 ms vs 3.28 ms
-//   per 12 layers), the same plus a per-sub-partition token that serialises the exp phases (3.71 ms),
-//   and a one-time stagger of the four chains (no effect).
+//   Also: P in shared memory with S_t(j+1) issued as soon as S_t(j) is in registers (3.57 ms vs 3.28 ms per 12
+//   layers); more variants are listed above the kernel.
 #include "vf_common.cuh"
 
 #include <math.h>
