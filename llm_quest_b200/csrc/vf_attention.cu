@@ -151,7 +151,9 @@ __device__ __forceinline__ int pair_bh(const AttnParams& p, int item, int m) {
 // 16-key chunks and running the ragged last query tile on one lane quarter only (no change at S=784: a key
 // step there is bound by the chain's serial latency, not by the amount of exponentials), and evaluating every 4th /
 // 3rd / 2nd pair of exponentials on the FMA pipe (Cody-Waite split + degree-3 minimax polynomial, packed f32x2:
-// 2414 / 2501 / 2813 us against 2296 at S=6272 — the softmax warps are short of issue slots, not of MUFU cycles).
+// 2414 / 2501 / 2813 us against 2296 at S=6272 — the softmax warps are short of issue slots, not of MUFU cycles), and
+// ex2.approx.ftz.bf16x2 for both exponentials of a pair (ptxas splits it into two MUFU.EX2.BF16: no packed MUFU on
+// sm_100a; 2479 us and twice the error).
 
 template <int FLAGS>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
