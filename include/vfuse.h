@@ -90,6 +90,21 @@ typedef struct {
    * "GEMM, then ncclAllGather of its output" for the sample-sharded path. `out` is ignored. */
   int32_t n_peers;         /* 0 = store to `out` only */
   void* peer_out[8];
+  /* LayerNorm folded into the two GEMMs around it (pre-LN block, qwen3_5_vision_model.py:195-238):
+   *   LN(x) @ W^T + b  =  rstd * (x @ (gamma.W)^T - mean * colsum) + (b + W beta),   colsum[n] = sum_k bf16(gamma_k W[n,k]).
+   * PRODUCER side (VF_EPI_BIAS_RES_F32, identity row map; also vf_patch_embed_ln): besides the fp32 row the epilogue
+   * writes its bf16 copy to ln_xb_out (the next GEMM's A operand) and, per 32-column block j, the partial row sums
+   * ln_stat_out[j * ln_stat_ld + row] = (sum x, sum x^2) as float2 — N/32 partials per row, no atomics, fixed order.
+   * vf_ln_row_stats() turns the partials into (mean, rstd) per row.
+   * CONSUMER side (VF_EPI_GELU_*_BF16, VF_EPI_QKV_ROPE_BF16): ln_row_stats holds (mean, rstd) of every row of A; the
+   * epilogue applies the identity above with ln_colsum [N] fp32. `bias` must already hold b + W beta and W must
+   * already be gamma-scaled (host side, once per weight). */
+  void* ln_xb_out;           /* bf16 [rows, ln_ldxb] or NULL */
+  int64_t ln_ldxb;
+  void* ln_stat_out;         /* float2 [N/32][ln_stat_ld] or NULL (required with ln_xb_out) */
+  int64_t ln_stat_ld;        /* rows per partial plane (>= M) */
+  const void* ln_row_stats;  /* float2 [M] (mean, rstd) or NULL */
+  const float* ln_colsum;    /* [N] fp32 (required with ln_row_stats) */
 } vf_epilogue;
 
 int vf_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, int32_t M, int32_t N,
@@ -111,6 +126,13 @@ int vf_patch_embed(const void* pixels, int32_t B, int32_t C, int32_t T, int32_t 
                    int32_t P, int32_t tp, const void* weight, const float* bias, const float* pos,
                    int64_t ld_pos, int32_t N, float* out, int64_t ldo, int64_t out_rows_per_sample,
                    int64_t out_row_off, void* stream);
+
+/* vf_patch_embed that also emits the producer side of the folded LayerNorm (see vf_epilogue.ln_xb_out): the bf16 copy
+ * of every output row and its N/32 partial (sum, sum of squares) — what the first block's norm1 + QKV GEMM consume. */
+int vf_patch_embed_ln(const void* pixels, int32_t B, int32_t C, int32_t T, int32_t H, int32_t W, int32_t P, int32_t tp,
+                      const void* weight, const float* bias, const float* pos, int64_t ld_pos, int32_t N, float* out,
+                      int64_t ldo, int64_t out_rows_per_sample, int64_t out_row_off, void* ln_xb_out, int64_t ln_ldxb,
+                      void* ln_stat_out, int64_t ln_stat_ld, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Fused bidirectional attention, head_dim 64, bf16 in/out, fp32 softmax (tcgen05 + TMEM).
@@ -155,6 +177,12 @@ int vf_attention_gqa_fwd(const void* q, int64_t ldq, int32_t q_col0, int32_t q_h
 int vf_layernorm(const void* x, int32_t in_dtype, int64_t ldx, const float* w, const float* b,
                  void* out, int32_t out_dtype, int64_t rows, int32_t D, float eps, int32_t variant,
                  int32_t merge, int32_t nh, int32_t nw, void* stream);
+
+/* (mean, rstd) per row from the partial sums a folded-LayerNorm producer epilogue left (vf_epilogue.ln_stat_out):
+ * partials float2 [parts][ld] -> out float2 [rows], mean = sum / D, rstd = rsqrt(max(sumsq / D - mean^2, 0) + eps).
+ * Summation order is fixed (part 0, 1, ...), so results do not depend on the batch a row sits in. */
+int vf_ln_row_stats(const void* partials, int32_t parts, int64_t ld, int64_t rows, int32_t D, float eps, void* out,
+                    void* stream);
 
 /* Part-1 class-token rows: out[b*S + 0, :] = cls[:] + pos[0, :]   (vit_model.py:86-87,145) */
 int vf_vit_cls_pos(const float* cls, const float* pos, float* out, int32_t B, int64_t rows_per_sample,

@@ -27,7 +27,7 @@ VF_EPI_SCATTER_BF16 = 6
 
 EXPORTS = [
     "vf_version", "vf_last_error", "vf_launch_count", "vf_launch_count_reset", "vf_gemm_bf16",
-    "vf_patch_embed", "vf_attention_fwd", "vf_attention_set_trace", "vf_attention_gqa_fwd", "vf_layernorm", "vf_vit_cls_pos", "vf_rope_apply",
+    "vf_patch_embed", "vf_patch_embed_ln", "vf_attention_fwd", "vf_attention_set_trace", "vf_attention_gqa_fwd", "vf_layernorm", "vf_ln_row_stats", "vf_vit_cls_pos", "vf_rope_apply",
     "vf_mrope_apply", "vf_mrope_apply_strided", "vf_mrope_position_ids", "vf_fuse_scan", "vf_embed_gather_scatter",
     "vf_cast_f32_to_bf16", "vf_cast_bf16_to_f32", "vf_preprocess_u8",
 ]
@@ -55,6 +55,12 @@ class vf_epilogue(C.Structure):
         ("dst_rows", C.c_void_p),
         ("n_peers", C.c_int32),
         ("peer_out", C.c_void_p * 8),
+        ("ln_xb_out", C.c_void_p),
+        ("ln_ldxb", C.c_int64),
+        ("ln_stat_out", C.c_void_p),
+        ("ln_stat_ld", C.c_int64),
+        ("ln_row_stats", C.c_void_p),
+        ("ln_colsum", C.c_void_p),
     ]
 
 
@@ -80,11 +86,14 @@ def lib() -> C.CDLL:
     sigs = {
         "vf_gemm_bf16": [vp, i64, vp, i64, i32, i32, i32, C.POINTER(vf_epilogue), vp],
         "vf_patch_embed": [vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, i64, i32, vp, i64, i64, i64, vp],
+        "vf_patch_embed_ln": [vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, i64, i32, vp, i64, i64, i64,
+                              vp, i64, vp, i64, vp],
         "vf_attention_fwd": [vp, vp, i32, i32, i32, f32, vp],
         "vf_attention_set_trace": [vp, i32, i32],
         "vf_attention_gqa_fwd": [vp, i64, i32, i32, vp, i64, vp, i64, vp, i64, vp, i64, i32, i32, i32, i32, i32, i32, i32,
                                  f32, i32, vp],
         "vf_layernorm": [vp, i32, i64, vp, vp, vp, i32, i64, i32, f32, i32, i32, i32, i32, vp],
+        "vf_ln_row_stats": [vp, i32, i64, i64, i32, f32, vp, vp],
         "vf_vit_cls_pos": [vp, vp, vp, i32, i64, i32, vp],
         "vf_rope_apply": [vp, vp, i32, i32, i32, i32, i32, vp, vp, i32, i64, vp, vp],
         "vf_mrope_apply": [vp, vp, i32, i32, i32, i32, i32, vp, vp, i32, i64, vp, i32, i32, i32, vp, f32, vp],
@@ -193,10 +202,13 @@ _EPI_NAMES = {0: "bias_bf16", 1: "bias_f32", 2: "bias_res_f32", 3: "gelu_tanh_bf
 # tensor-level wrappers
 # ------------------------------------------------------------------------------------------------
 def gemm(a, w, mode, out, bias=None, res=None, rope=None, dst_rows=None, grp_rows=0, grp_stride=0, row_off=0,
-         peer_ptrs=None):
+         peer_ptrs=None, ln_out=None, ln_in=None):
     """out = epilogue(a @ w.T). a [M,K] bf16 (row stride free), w [N,K] bf16, see vf_epilogue_mode.
     peer_ptrs: device pointers (ints) of up to 8 destination buffers shaped like `out` (fused all-gather: the rows
-    are stored to every one of them, `out` only provides dtype and row pitch)."""
+    are stored to every one of them, `out` only provides dtype and row pitch).
+    ln_out = (xb bf16 [rows, N], stat fp32 [N/32, rows, 2]): LayerNorm producer side (bias_res_f32 only).
+    ln_in = (row_stats fp32 [M, 2] (mean, rstd) from ln_row_stats(), colsum fp32 [N]): LayerNorm consumer side
+    (GELU / QKV+RoPE epilogues); `w` and `bias` must be the folded ones (qwen3_5_vision_model._fold_ln)."""
     _require_cuda(a, w, out, bias, res, dst_rows)
     assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and a.dim() == 2 and w.dim() == 2
     assert a.stride(1) == 1 and w.stride(1) == 1 and out.stride(-1) == 1
@@ -225,24 +237,55 @@ def gemm(a, w, mode, out, bias=None, res=None, rope=None, dst_rows=None, grp_row
             ep.peer_out[i] = int(ptr)
     if bias is not None:
         assert bias.dtype == torch.float32 and bias.is_contiguous() and bias.numel() == N
+    if ln_out is not None:
+        xb, stat = ln_out
+        _require_cuda(xb, stat)
+        assert xb.dtype == torch.bfloat16 and xb.stride(-1) == 1 and stat.dtype == torch.float32 and stat.is_contiguous()
+        assert stat.dim() == 3 and stat.shape[0] == N // 32 and stat.shape[2] == 2
+        ep.ln_xb_out, ep.ln_ldxb, ep.ln_stat_out, ep.ln_stat_ld = xb.data_ptr(), xb.stride(-2), stat.data_ptr(), stat.shape[1]
+    if ln_in is not None:
+        row_stats, colsum = ln_in
+        _require_cuda(row_stats, colsum)
+        assert row_stats.dtype == torch.float32 and row_stats.is_contiguous() and row_stats.shape == (M, 2)
+        assert colsum.dtype == torch.float32 and colsum.is_contiguous() and colsum.numel() == N
+        ep.ln_row_stats, ep.ln_colsum = row_stats.data_ptr(), colsum.data_ptr()
     with _timed("gemm_" + _EPI_NAMES.get(mode, str(mode)), flops=2.0 * M * N * K):
         check(lib().vf_gemm_bf16(a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), M, N, K, C.byref(ep),
                                  _stream()), "vf_gemm_bf16")
     return out
 
 
-def patch_embed(pixels, weight2d, bias, pos, out, P, tp, out_rows_per_sample, out_row_off):
-    """pixels bf16 [B,C,T,H,W]; weight2d bf16 [N, C*tp*P*P]; out fp32 [rows, N] (see vfuse.h)."""
+def ln_row_stats(stat, D, eps, out):
+    """partials fp32 [parts, rows, 2] (a producer's ln_out stat) -> out fp32 [rows, 2] = (mean, rstd)."""
+    _require_cuda(stat, out)
+    assert stat.dtype == torch.float32 and stat.is_contiguous() and stat.dim() == 3 and stat.shape[2] == 2
+    assert out.dtype == torch.float32 and out.is_contiguous() and out.shape == (stat.shape[1], 2)
+    with _timed("ln_row_stats", bytes=stat.numel() * 4 + out.numel() * 4):
+        check(lib().vf_ln_row_stats(stat.data_ptr(), stat.shape[0], stat.shape[1], stat.shape[1], D, float(eps),
+                                    out.data_ptr(), _stream()), "vf_ln_row_stats")
+    return out
+
+
+def patch_embed(pixels, weight2d, bias, pos, out, P, tp, out_rows_per_sample, out_row_off, ln_out=None):
+    """pixels bf16 [B,C,T,H,W]; weight2d bf16 [N, C*tp*P*P]; out fp32 [rows, N] (see vfuse.h).
+    ln_out = (xb bf16 [rows, N], stat fp32 [N/32, rows, 2]): also emit the folded-LayerNorm producer outputs."""
     _require_cuda(pixels, weight2d, out)
     assert pixels.dtype == torch.bfloat16 and pixels.is_contiguous() and pixels.dim() == 5
     B, Cc, T, H, W = pixels.shape
     N = weight2d.shape[0]
+    xb_p = xb_ld = st_p = st_ld = 0
+    if ln_out is not None:
+        xb, stat = ln_out
+        _require_cuda(xb, stat)
+        assert xb.dtype == torch.bfloat16 and xb.stride(-1) == 1 and stat.dtype == torch.float32 and stat.is_contiguous()
+        assert stat.dim() == 3 and stat.shape[0] == N // 32 and stat.shape[2] == 2
+        xb_p, xb_ld, st_p, st_ld = xb.data_ptr(), xb.stride(-2), stat.data_ptr(), stat.shape[1]
     with _timed("patch_embed", flops=2.0 * B * (T // tp) * (H // P) * (W // P) * N * weight2d.shape[1]):
         check(
-            lib().vf_patch_embed(pixels.data_ptr(), B, Cc, T, H, W, P, tp, weight2d.data_ptr(), _p(bias), _p(pos),
-                                 pos.stride(0) if pos is not None else 0, N, out.data_ptr(), out.stride(-2),
-                                 out_rows_per_sample, out_row_off, _stream()),
-            "vf_patch_embed",
+            lib().vf_patch_embed_ln(pixels.data_ptr(), B, Cc, T, H, W, P, tp, weight2d.data_ptr(), _p(bias), _p(pos),
+                                    pos.stride(0) if pos is not None else 0, N, out.data_ptr(), out.stride(-2),
+                                    out_rows_per_sample, out_row_off, xb_p, xb_ld, st_p, st_ld, _stream()),
+            "vf_patch_embed_ln",
         )
     return out
 

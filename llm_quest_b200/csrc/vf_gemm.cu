@@ -65,6 +65,13 @@ struct GemmParams {
   int Tp, T, C, tp, P; // frames after temporal merge, raw frames, channels, temporal patch, patch
   const float* pos;
   long long ld_pos;
+  // LayerNorm folded into the neighbouring GEMMs (see vf_epilogue in vfuse.h)
+  __nv_bfloat16* ln_xb;      // producer: bf16 copy of the fp32 output rows
+  long long ln_ldxb;
+  float2* ln_stat_out;       // producer: [N/32][ln_stat_ld] partial (sum, sum of squares)
+  long long ln_stat_ld;
+  const float2* ln_row_stats;  // consumer: [M] (mean, rstd)
+  const float* ln_colsum;      // consumer: [N]
 };
 
 // CG = 1: one CTA per 128 x BN tile. CG = 2: a CTA pair (cta_group::2) per 256 x BN tile — each CTA stages
@@ -284,6 +291,11 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
       return v;
     };
 
+    auto write_staged2 = [&](uint32_t st, int rr, float a, float b) {   // first 8 bytes of the slot read_staged(rr) returns
+      asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(st + rr * 128 + ((cl ^ (rr & 7)) << 4)), "f"(a), "f"(b)
+                   : "memory");
+    };
+
     // Residual epilogue: the fp32 residual slab of a tile (128 KB) is pulled into L2 one tile ahead, while
     // the tensor pipe is still busy with the current one, so the epilogue's loads are L2 hits instead of
     // serialised DRAM round trips (measured: the proj GEMM, K=768, was bound by exactly that latency).
@@ -313,6 +325,7 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
       // One integer division per tile at most; the other rows follow incrementally.
       long long orow[8];
       int aux[8];  // patch: spatial index (pos-embed row); rope: cos/sin table row
+      [[maybe_unused]] long long lane_orow = -1;   // output row of tile row quarter*32 + lane (folded-LN producer)
       {
         const int r0 = quarter * 32 + rl;
         if constexpr (PATCH) {
@@ -322,6 +335,11 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
           const int tpr = t % p.Tp;
           const int b = t / p.Tp;
           const long long base = (long long)b * p.grp_stride + p.row_off + (long long)tpr * p.nh * p.nw;
+          {
+            const int rq = quarter * 32 + lane;
+            const int ph = phb * 16 + (rq >> 3), pw = pwb * 8 + (rq & 7);
+            if (ph < p.nh && pw < p.nw) lane_orow = base + ph * p.nw + pw;
+          }
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int r_local = r0 + 4 * i;          // tile rows are a 16 x 8 rectangle of patches
@@ -333,6 +351,7 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
           }
         } else {
           const int m0 = m_blk * BM + r0;
+          if (m_blk * BM + quarter * 32 + lane < p.M) lane_orow = m_blk * BM + quarter * 32 + lane;   // identity map
           int q = 0, rem = 0;                         // remap / rope: running quotient and remainder
           if (EPI == VF_EPI_QKV_ROPE_BF16) rem = m0 % p.rope_period;
           else if (p.grp_rows > 0) { q = m0 / p.grp_rows; rem = m0 - q * p.grp_rows; }
@@ -371,6 +390,20 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
       };
       load_res(0);
 
+      // LayerNorm folded into this GEMM (consumer side): lane L fetches (mean, rstd) of tile row quarter*32 + L while the
+      // tensor pipe is still busy with the tile; the coalesced mapping below gets the values of its rows by shuffle.
+      [[maybe_unused]] float ln_mu = 0.f, ln_rs = 0.f;
+      [[maybe_unused]] const bool ln_in = p.ln_row_stats != nullptr;
+      if constexpr (EPI == VF_EPI_GELU_TANH_BF16 || EPI == VF_EPI_GELU_ERF_BF16 || EPI == VF_EPI_QKV_ROPE_BF16) {
+        if (ln_in) {
+          const int m = m_blk * BM + quarter * 32 + lane;
+          if (m < p.M) {
+            const float2 t = __ldg(p.ln_row_stats + m);
+            ln_mu = t.x; ln_rs = t.y;
+          }
+        }
+      }
+
       wait_or_trap(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + chalf * COLS_PER_WARP;
@@ -405,17 +438,29 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
           __syncwarp();
           if (hc >= p.N) continue;
           const bool rot = hc < p.rope_cols;
-          float4 b1 = make_float4(0.f, 0.f, 0.f, 0.f), b2 = b1;
+          float4 b1 = make_float4(0.f, 0.f, 0.f, 0.f), b2 = b1, cs1 = b1, cs2 = b1;
           if (p.bias) {
             b1 = __ldg(reinterpret_cast<const float4*>(p.bias + hc) + cl);
             b2 = __ldg(reinterpret_cast<const float4*>(p.bias + hc + 32) + cl);
+          }
+          if (ln_in) {
+            cs1 = __ldg(reinterpret_cast<const float4*>(p.ln_colsum + hc) + cl);
+            cs2 = __ldg(reinterpret_cast<const float4*>(p.ln_colsum + hc + 32) + cl);
           }
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int rr = rl + 4 * i;
             float4 x1 = x1s[i], x2 = read_staged(stA, rr);
-            x1.x += b1.x; x1.y += b1.y; x1.z += b1.z; x1.w += b1.w;
-            x2.x += b2.x; x2.y += b2.y; x2.z += b2.z; x2.w += b2.w;
+            if (ln_in) {   // rstd * (acc - mean * colsum) + bias'
+              const float mu = __shfl_sync(0xffffffffu, ln_mu, rr), rs = __shfl_sync(0xffffffffu, ln_rs, rr);
+              x1.x = fmaf(rs, fmaf(-mu, cs1.x, x1.x), b1.x); x1.y = fmaf(rs, fmaf(-mu, cs1.y, x1.y), b1.y);
+              x1.z = fmaf(rs, fmaf(-mu, cs1.z, x1.z), b1.z); x1.w = fmaf(rs, fmaf(-mu, cs1.w, x1.w), b1.w);
+              x2.x = fmaf(rs, fmaf(-mu, cs2.x, x2.x), b2.x); x2.y = fmaf(rs, fmaf(-mu, cs2.y, x2.y), b2.y);
+              x2.z = fmaf(rs, fmaf(-mu, cs2.z, x2.z), b2.z); x2.w = fmaf(rs, fmaf(-mu, cs2.w, x2.w), b2.w);
+            } else {
+              x1.x += b1.x; x1.y += b1.y; x1.z += b1.z; x1.w += b1.w;
+              x2.x += b2.x; x2.y += b2.y; x2.z += b2.z; x2.w += b2.w;
+            }
             const float4 c = rot ? cv[i] : make_float4(1.f, 1.f, 1.f, 1.f);
             const float4 sn = rot ? sv[i] : make_float4(0.f, 0.f, 0.f, 0.f);
             float4 y1, y2;
@@ -460,6 +505,10 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
           if (fast) {
             float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
             if (p.bias) bv = __ldg(reinterpret_cast<const float4*>(p.bias + cc));
+            [[maybe_unused]] float4 csv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if constexpr (EPI == VF_EPI_GELU_TANH_BF16 || EPI == VF_EPI_GELU_ERF_BF16)
+              if (ln_in) csv = __ldg(reinterpret_cast<const float4*>(p.ln_colsum + cc));
+            [[maybe_unused]] const bool ln_out = p.ln_xb != nullptr;
             // residual / pos-embed values of all 8 rows are fetched up front: they may alias `out`, so
             // the compiler cannot hoist them across the stores by itself
             if constexpr (PATCH) {
@@ -474,8 +523,25 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
               for (int i = 0; i < 8; ++i) {
                 const float4 x = read_staged(stA, rl + 4 * i);
                 float v[4] = {x.x + bv.x, x.y + bv.y, x.z + bv.z, x.w + bv.w};
+                if constexpr (EPI == VF_EPI_GELU_TANH_BF16 || EPI == VF_EPI_GELU_ERF_BF16) {
+                  if (ln_in) {   // rstd * (acc - mean * colsum) + bias'
+                    const float mu = __shfl_sync(0xffffffffu, ln_mu, rl + 4 * i);
+                    const float rs = __shfl_sync(0xffffffffu, ln_rs, rl + 4 * i);
+                    v[0] = fmaf(rs, fmaf(-mu, csv.x, x.x), bv.x); v[1] = fmaf(rs, fmaf(-mu, csv.y, x.y), bv.y);
+                    v[2] = fmaf(rs, fmaf(-mu, csv.z, x.z), bv.z); v[3] = fmaf(rs, fmaf(-mu, csv.w, x.w), bv.w);
+                  }
+                }
                 if constexpr (EPI == VF_EPI_BIAS_RES_F32 || PATCH) {
                   v[0] += ex[i].x; v[1] += ex[i].y; v[2] += ex[i].z; v[3] += ex[i].w;
+                  if (ln_out) {
+                    // producer side of the folded LayerNorm: bf16 copy of the row (the next GEMM's A operand), and this
+                    // lane's share of the row's (sum, sum of squares) parked in the staging slot it has just read
+                    write_staged2(stA, rl + 4 * i, (v[0] + v[1]) + (v[2] + v[3]),
+                                  fmaf(v[0], v[0], fmaf(v[1], v[1], fmaf(v[2], v[2], v[3] * v[3]))));
+                    if (!decltype(guarded)::value || orow[i] >= 0)
+                      *reinterpret_cast<uint2*>(p.ln_xb + orow[i] * p.ln_ldxb + cc) =
+                          make_uint2(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]));
+                  }
                 }
                 if constexpr (EPI == VF_EPI_GELU_TANH_BF16) {
 #pragma unroll
@@ -507,6 +573,24 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
             };
             if (rows_all_valid) do_rows(std::false_type{});
             else do_rows(std::true_type{});
+            if constexpr (EPI == VF_EPI_BIAS_RES_F32 || PATCH) {
+              if (ln_out) {
+                // lane L adds up the 8 shares of tile row quarter*32 + L (no shuffles, no extra live registers) and the
+                // warp stores the 32 partial sums of this 32-column block with one coalesced 256-byte store
+                __syncwarp();
+                float s_ = 0.f, q_ = 0.f;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                  float a_, b_;
+                  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];"
+                               : "=f"(a_), "=f"(b_)
+                               : "r"(stA + lane * 128 + ((k ^ (lane & 7)) << 4))
+                               : "memory");
+                  s_ += a_; q_ += b_;
+                }
+                if (lane_orow >= 0) p.ln_stat_out[(long long)(cc >> 5) * p.ln_stat_ld + lane_orow] = make_float2(s_, q_);
+              }
+            }
             if (c + 1 < COLS_PER_WARP / 32) load_res(c + 1);
           } else {
             // generic path (unaligned rows or N % 4 != 0, e.g. a 10-class head): scalar, per-element guards
@@ -660,6 +744,31 @@ extern "C" int vf_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t l
     p.n_peers = ep->n_peers;
   }
 
+  if (ep->ln_xb_out || ep->ln_stat_out) {
+    VF_REQUIRE(ep->mode == VF_EPI_BIAS_RES_F32 && ep->grp_rows <= 0, VF_ERR_ARG,
+               "vf_gemm_bf16: ln_xb_out / ln_stat_out need the bias_res_f32 epilogue with the identity row map");
+    VF_REQUIRE(ep->ln_xb_out && ep->ln_stat_out && ep->ln_stat_ld >= M, VF_ERR_ARG,
+               "vf_gemm_bf16: ln_xb_out, ln_stat_out and ln_stat_ld >= M go together");
+    VF_REQUIRE(vec_ok && (N % 32) == 0 && ep->ln_ldxb >= N && (ep->ln_ldxb % 4) == 0 &&
+                   (reinterpret_cast<uintptr_t>(ep->ln_xb_out) & 7) == 0 &&
+                   (reinterpret_cast<uintptr_t>(ep->ln_stat_out) & 7) == 0,
+               VF_ERR_ALIGN, "vf_gemm_bf16: folded LayerNorm (producer) needs aligned rows and N %% 32 == 0");
+    p.ln_xb = static_cast<__nv_bfloat16*>(ep->ln_xb_out);
+    p.ln_ldxb = ep->ln_ldxb;
+    p.ln_stat_out = static_cast<float2*>(ep->ln_stat_out);
+    p.ln_stat_ld = ep->ln_stat_ld;
+  }
+  if (ep->ln_row_stats) {
+    VF_REQUIRE(ep->mode == VF_EPI_GELU_TANH_BF16 || ep->mode == VF_EPI_GELU_ERF_BF16 || ep->mode == VF_EPI_QKV_ROPE_BF16,
+               VF_ERR_ARG, "vf_gemm_bf16: ln_row_stats needs a GELU or QKV+RoPE epilogue");
+    VF_REQUIRE(ep->ln_colsum, VF_ERR_ARG, "vf_gemm_bf16: folded LayerNorm (consumer) needs ln_colsum");
+    VF_REQUIRE(vec_ok && (N & 3) == 0 && (reinterpret_cast<uintptr_t>(ep->ln_colsum) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(ep->ln_row_stats) & 7) == 0,
+               VF_ERR_ALIGN, "vf_gemm_bf16: folded LayerNorm (consumer) needs aligned rows and N %% 4 == 0");
+    p.ln_row_stats = static_cast<const float2*>(ep->ln_row_stats);
+    p.ln_colsum = ep->ln_colsum;
+  }
+
   // CTA pairs for every 256-wide problem with at least one full pair of row blocks per SM pair
   // (VF_GEMM_CG=1 forces the single-CTA kernel: development A/B switch)
   static int cg_env = -1;
@@ -697,6 +806,16 @@ extern "C" int vf_patch_embed(const void* pixels, int32_t B, int32_t C, int32_t 
                               const float* bias, const float* pos, int64_t ld_pos, int32_t N,
                               float* out, int64_t ldo, int64_t out_rows_per_sample,
                               int64_t out_row_off, void* stream) {
+  return vf_patch_embed_ln(pixels, B, C, T, H, W, P, tp, weight, bias, pos, ld_pos, N, out, ldo, out_rows_per_sample,
+                           out_row_off, nullptr, 0, nullptr, 0, stream);
+}
+
+extern "C" int vf_patch_embed_ln(const void* pixels, int32_t B, int32_t C, int32_t T, int32_t H,
+                                 int32_t W, int32_t P, int32_t tp, const void* weight,
+                                 const float* bias, const float* pos, int64_t ld_pos, int32_t N,
+                                 float* out, int64_t ldo, int64_t out_rows_per_sample,
+                                 int64_t out_row_off, void* ln_xb_out, int64_t ln_ldxb, void* ln_stat_out,
+                                 int64_t ln_stat_ld, void* stream) {
   VF_REQUIRE(pixels && weight && out, VF_ERR_ARG, "vf_patch_embed: null pointer");
   VF_REQUIRE(B > 0 && C > 0 && T > 0 && H > 0 && W > 0 && N > 0, VF_ERR_ARG, "vf_patch_embed: bad shape");
   VF_REQUIRE(P == 16, VF_ERR_ARG,
@@ -733,6 +852,18 @@ extern "C" int vf_patch_embed(const void* pixels, int32_t B, int32_t C, int32_t 
   p.out = out; p.ldo = ldo;
   p.grp_stride = out_rows_per_sample; p.row_off = out_row_off;
   p.vec_ok = 1;
+  if (ln_xb_out || ln_stat_out) {
+    const int64_t rows = (int64_t)(B - 1) * out_rows_per_sample + out_row_off + (int64_t)Tp * nh * nw;
+    VF_REQUIRE(ln_xb_out && ln_stat_out && ln_stat_ld >= rows, VF_ERR_ARG,
+               "vf_patch_embed_ln: ln_xb_out, ln_stat_out and ln_stat_ld >= output rows go together");
+    VF_REQUIRE((N % 32) == 0 && ln_ldxb >= N && (ln_ldxb % 4) == 0 && (reinterpret_cast<uintptr_t>(ln_xb_out) & 7) == 0 &&
+                   (reinterpret_cast<uintptr_t>(ln_stat_out) & 7) == 0,
+               VF_ERR_ALIGN, "vf_patch_embed_ln: needs N %% 32 == 0 and aligned xb rows");
+    p.ln_xb = static_cast<__nv_bfloat16*>(ln_xb_out);
+    p.ln_ldxb = ln_ldxb;
+    p.ln_stat_out = static_cast<float2*>(ln_stat_out);
+    p.ln_stat_ld = ln_stat_ld;
+  }
 
   CUtensorMap tmA, tmB;
   {

@@ -75,6 +75,32 @@ def _f32(cache: _Packed, key, p):
     return cache.get(key, [p], lambda: p.detach().to(torch.float32).contiguous())
 
 
+def _fold_ln(cache: _Packed, key, lin: nn.Linear, norm: nn.LayerNorm):
+    """LayerNorm folded into the Linear that follows it:
+        LN(x) @ W^T + b = rstd * (x @ (gamma . W)^T - mean * colsum) + (b + W beta)
+    Returns (bf16 gamma-scaled weight, fp32 folded bias, fp32 colsum of the ROUNDED weight — the GEMM multiplies by
+    the rounded one, so the mean term must cancel against exactly that)."""
+
+    def build():
+        w = lin.weight.detach().to(torch.float32)
+        wf = (w * norm.weight.detach().to(torch.float32)[None, :]).to(torch.bfloat16).contiguous()
+        colsum = wf.to(torch.float32).sum(dim=1).contiguous()
+        b = w @ norm.bias.detach().to(torch.float32)
+        if lin.bias is not None:
+            b = b + lin.bias.detach().to(torch.float32)
+        return wf, b.contiguous(), colsum
+
+    return cache.get(key, [lin.weight, lin.bias, norm.weight, norm.bias], build)
+
+
+def ln_fusion_mode() -> int:
+    """How much LayerNorm is folded into the GEMMs of a block (VF_LN_FUSE): 0 = none (stand-alone kernels), 1 = norm1
+    only (lin2 / patch embedding produce, QKV consumes), 2 = norm1 and norm2 (proj produces, lin1 consumes)."""
+    import os
+
+    return int(os.environ.get("VF_LN_FUSE", "1"))
+
+
 def _as_2d_bf16(x: torch.Tensor) -> torch.Tensor:
     return _lib.to_bf16(x.reshape(-1, x.shape[-1]))
 
@@ -105,8 +131,9 @@ class PatchEmbedding3D(nn.Module):
             f"Input time shape {time} is not divisible by temporal_patch_size {self.temporal_patch_size}"
         )
 
-    def embed_into(self, x, pos=None):
-        """fp32 [B*S, D] = conv(x) + bias (+ pos[token % n]); the fused entry the tower uses."""
+    def embed_into(self, x, pos=None, ln_work=None):
+        """fp32 [B*S, D] = conv(x) + bias (+ pos[token % n]); the fused entry the tower uses.
+        ln_work: callable (rows, D) -> (xb, stat) buffers for the folded-LayerNorm producer outputs, or None."""
         self._check(x)
         B, _, T, H, W = x.shape
         P, tp = self.patch_size, self.temporal_patch_size
@@ -115,7 +142,8 @@ class PatchEmbedding3D(nn.Module):
         w = _w_bf16(self._packed, "w", self.conv_proj.weight, (D, -1))
         bias = _f32(self._packed, "b", self.conv_proj.bias)
         out = torch.empty((B * S, D), dtype=torch.float32, device=x.device)
-        _lib.patch_embed(_lib.to_bf16(x), w, bias, pos, out, P, tp, S, 0)
+        _lib.patch_embed(_lib.to_bf16(x), w, bias, pos, out, P, tp, S, 0,
+                         ln_out=ln_work(B * S, D) if ln_work is not None else None)
         return out, B, S
 
     def forward(self, x):
@@ -172,13 +200,16 @@ class Qwen3_5VisionAttention(nn.Module):
         if self.head_dim != 64:
             raise VFuseError(f"the fused attention / RoPE kernels are built for head_dim 64, got {self.head_dim}")
 
-    def attend(self, h2d, B, S, rope):
-        """h2d bf16 [B*S, D] -> context bf16 [B*S, D]. rope = (cos_half, sin_half, period)."""
+    def attend(self, h2d, B, S, rope, folded=None, ln_in=None):
+        """h2d bf16 [B*S, D] -> context bf16 [B*S, D]. rope = (cos_half, sin_half, period).
+        folded/ln_in: norm1 folded into the QKV GEMM — h2d is then the bf16 copy of the un-normalised stream."""
         self._require_hd64()
         wqkv, bqkv, _, _ = self.packed()
+        if folded is not None:
+            wqkv, bqkv = folded
         D = self.d_in
         qkv = torch.empty((B * S, 3 * D), dtype=torch.bfloat16, device=h2d.device)
-        _lib.gemm(h2d, wqkv, VF_EPI_QKV_ROPE_BF16, qkv, bias=bqkv, rope=(rope[0], rope[1], rope[2], 2 * D))
+        _lib.gemm(h2d, wqkv, VF_EPI_QKV_ROPE_BF16, qkv, bias=bqkv, rope=(rope[0], rope[1], rope[2], 2 * D), ln_in=ln_in)
         ctx = torch.empty((B * S, D), dtype=torch.bfloat16, device=h2d.device)
         _lib.attention(qkv, ctx, B, S, self.num_heads, self.head_dim**-0.5)
         return ctx
@@ -207,20 +238,41 @@ class Qwen3_5VisionTransformerBlock(nn.Module):
         self.ffn = Qwen3_5VisionFFN(cfg)
         self._packed = _Packed()
 
-    def run_(self, x2d, B, S, rope, work):
-        """In-place update of the fp32 residual stream x2d [B*S, D]; `work` holds reusable buffers."""
+    def run_(self, x2d, B, S, rope, work, ln1_ready=False, emit_next=False):
+        """In-place update of the fp32 residual stream x2d [B*S, D]; `work` holds reusable buffers.
+
+        With work["stat"] present both LayerNorms are folded into the GEMMs around them (vf_epilogue.ln_*): the GEMM
+        that produces x also writes its bf16 copy to work["h"] and per-row partial sums to work["stat"] (finalised into
+        work["rows"] = (mean, rstd) by a tiny kernel), the GEMM that consumes LN(x) multiplies the bf16 copy by the
+        gamma-scaled weight and normalises in its epilogue. ln1_ready:
+        the previous producer (patch embedding or the previous block's lin2) already left h/stat for norm1;
+        emit_next: this block's lin2 leaves them for the next block."""
         c = self._packed
-        n1w, n1b = _f32(c, "n1w", self.norm1.weight), _f32(c, "n1b", self.norm1.bias)
-        n2w, n2b = _f32(c, "n2w", self.norm2.weight), _f32(c, "n2b", self.norm2.bias)
         _, _, wo, bo = self.att.packed()
         w1, b1, w2, b2 = self.ffn.packed()
-        h, g = work["h"], work["g"]
-        _lib.layernorm(x2d, n1w, n1b, h, self.norm1.eps)
-        ctx = self.att.attend(h, B, S, rope)
+        h, g, stat, rows = work["h"], work["g"], work.get("stat"), work.get("rows")
+        D = x2d.shape[1]
+        if stat is not None and ln1_ready:
+            wq, bq, csq = _fold_ln(c, "fold_qkv", self.att.qkv, self.norm1)
+            _lib.ln_row_stats(stat, D, self.norm1.eps, rows)
+            ctx = self.att.attend(h, B, S, rope, folded=(wq, bq), ln_in=(rows, csq))
+        else:
+            n1w, n1b = _f32(c, "n1w", self.norm1.weight), _f32(c, "n1b", self.norm1.bias)
+            _lib.layernorm(x2d, n1w, n1b, h, self.norm1.eps)
+            ctx = self.att.attend(h, B, S, rope)
+        nxt = (h, stat) if emit_next else None
+        if stat is not None and work.get("fold_norm2"):
+            w1f, b1f, cs1 = _fold_ln(c, "fold_lin1", self.ffn.lin1, self.norm2)
+            _lib.gemm(ctx, wo, VF_EPI_BIAS_RES_F32, x2d, bias=bo, res=x2d, ln_out=(h, stat))
+            _lib.ln_row_stats(stat, D, self.norm2.eps, rows)
+            _lib.gemm(h, w1f, VF_EPI_GELU_TANH_BF16, g, bias=b1f, ln_in=(rows, cs1))
+            _lib.gemm(g, w2, VF_EPI_BIAS_RES_F32, x2d, bias=b2, res=x2d, ln_out=nxt)
+            return
+        n2w, n2b = _f32(c, "n2w", self.norm2.weight), _f32(c, "n2b", self.norm2.bias)
         _lib.gemm(ctx, wo, VF_EPI_BIAS_RES_F32, x2d, bias=bo, res=x2d)
         _lib.layernorm(x2d, n2w, n2b, h, self.norm2.eps)
         _lib.gemm(h, w1, VF_EPI_GELU_TANH_BF16, g, bias=b1)
-        _lib.gemm(g, w2, VF_EPI_BIAS_RES_F32, x2d, bias=b2, res=x2d)
+        _lib.gemm(g, w2, VF_EPI_BIAS_RES_F32, x2d, bias=b2, res=x2d, ln_out=nxt)
 
     def forward(self, x, cos, sin):
         _forward_only_guard(self)
@@ -345,17 +397,28 @@ class Qwen3_5VisionModel(nn.Module):
         if not x.is_cuda:
             raise VFuseError("Qwen3_5VisionModel (llm_quest_b200) runs on CUDA sm_100a only; got a CPU tensor")
         pos = _f32(self._packed, "pos", self.pos_embed.weight)
-        x2d, B, S = self.patch_embed.embed_into(x, pos)
+        work = {}
+        mode = ln_fusion_mode()
+        fuse = mode > 0 and len(self.blocks) > 0 and self.pos_embed.embedding_dim % 32 == 0
+        work["fold_norm2"] = mode > 1
+
+        def ln_work(rows, D):
+            work["h"] = torch.empty((rows, D), dtype=torch.bfloat16, device=x.device)
+            work["stat"] = torch.empty((D // 32, rows, 2), dtype=torch.float32, device=x.device)
+            work["rows"] = torch.empty((rows, 2), dtype=torch.float32, device=x.device)
+            return work["h"], work["stat"]
+
+        x2d, B, S = self.patch_embed.embed_into(x, pos, ln_work if fuse else None)
         cos_h, sin_h = self._rope_half(x.device)
         rope = (cos_h, sin_h, self.n_spatial_patches)
         D = x2d.shape[1]
-        work = {
-            "h": torch.empty((B * S, D), dtype=torch.bfloat16, device=x.device),
-            "g": torch.empty((B * S, self.blocks[0].ffn.lin1.out_features), dtype=torch.bfloat16, device=x.device)
-            if len(self.blocks) else None,
-        }
-        for block in self.blocks:
-            block.run_(x2d, B, S, rope, work)
+        if not fuse:
+            work["h"] = torch.empty((B * S, D), dtype=torch.bfloat16, device=x.device)
+        if len(self.blocks):
+            work["g"] = torch.empty((B * S, self.blocks[0].ffn.lin1.out_features), dtype=torch.bfloat16, device=x.device)
+        last = len(self.blocks) - 1
+        for i, block in enumerate(self.blocks):
+            block.run_(x2d, B, S, rope, work, ln1_ready=fuse, emit_next=fuse and i < last)
         return x2d, B, S
 
     def forward(self, x, out=None, dst_rows=None, gather=None):

@@ -131,6 +131,81 @@ def test_gemm_row_remap_and_scatter(L):
     assert (got[untouched] == 0).all()
 
 
+def _fold(w, b, gamma, beta):
+    """host side of the folded LayerNorm (qwen3_5_vision_model._fold_ln restated for the test)"""
+    wf = bf(w * gamma[None, :])
+    return wf, (b + w @ beta).contiguous(), wf.float().sum(1).contiguous()
+
+
+@pytest.mark.parametrize("M", [777, 1024])
+def test_gemm_folded_layernorm_producer(L, M):
+    """bias_res_f32 with ln_out: bf16 copy of the rows + per-32-column partial (sum, sum of squares)."""
+    N, K = 768, 256
+    a, w, b = bf(rnd(M, K, seed=60)), bf(rnd(N, K, seed=61, scale=0.05)), rnd(N, seed=62)
+    res = rnd(M, N, seed=63) + 0.3
+    x = dev(res.clone())
+    xb = torch.zeros((M, N), dtype=torch.bfloat16, device="cuda")
+    stat = torch.full((N // 32, M, 2), float("nan"), device="cuda")
+    L.gemm(dev(a), dev(w), L.VF_EPI_BIAS_RES_F32, x, bias=dev(b), res=x, ln_out=(xb, stat))
+    ref = a.float() @ w.float().t() + b + res
+    check_close(x, ref, tol=2e-3, what="producer fp32 rows")
+    assert torch.equal(xb.cpu(), bf(x.cpu())), "bf16 copy is not the rounding of the fp32 row"
+    blocks = x.cpu().view(M, N // 32, 32)
+    torch.testing.assert_close(stat[:, :, 0].cpu().t(), blocks.sum(-1), rtol=1e-5, atol=1e-4)
+    torch.testing.assert_close(stat[:, :, 1].cpu().t(), (blocks * blocks).sum(-1), rtol=1e-5, atol=1e-4)
+
+
+@pytest.mark.parametrize("mode", ["tanh", "erf", "qkv"])
+def test_gemm_folded_layernorm_consumer(L, mode):
+    """producer -> consumer chain equals LayerNorm followed by the plain GEMM (oracle: fp32 LN + Linear)."""
+    nh, nw, B = 6, 5, 9
+    n = nh * nw
+    M, D = B * n, 768
+    N = 3 * D if mode == "qkv" else 1024
+    a, w0, b0 = bf(rnd(M, 128, seed=70)), bf(rnd(D, 128, seed=71, scale=0.1)), rnd(D, seed=72)
+    res = rnd(M, D, seed=73) * 2.0 + 0.5          # non-zero row means: the mean term must cancel
+    gamma, beta = 1.0 + 0.2 * rnd(D, seed=74), 0.1 * rnd(D, seed=75)
+    w, b = rnd(N, D, seed=76, scale=0.05), rnd(N, seed=77)
+    x = dev(res.clone())
+    xb = torch.empty((M, D), dtype=torch.bfloat16, device="cuda")
+    stat = torch.empty((D // 32, M, 2), device="cuda")
+    L.gemm(dev(a), dev(w0), L.VF_EPI_BIAS_RES_F32, x, bias=dev(b0), res=x, ln_out=(xb, stat))
+    wf, bfold, cs = _fold(w, b, gamma, beta)
+    xr = x.cpu()
+    rows = torch.empty((M, 2), device="cuda")
+    L.ln_row_stats(stat, D, 1e-6, rows)
+    torch.testing.assert_close(rows[:, 0].cpu(), xr.mean(1), rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(rows[:, 1].cpu(), (xr.var(1, unbiased=False) + 1e-6).rsqrt(), rtol=1e-4, atol=1e-5)
+    lin = torch.nn.functional.layer_norm(xr, (D,), gamma, beta, 1e-6) @ w.t() + b
+    out = torch.zeros((M, N), dtype=torch.bfloat16, device="cuda")
+    if mode == "qkv":
+        cos, sin = VO.axial_rope_tables(10_000, 64, nh, nw)
+        L.gemm(xb, dev(wf), L.VF_EPI_QKV_ROPE_BF16, out, bias=dev(bfold), ln_in=(rows, dev(cs)),
+               rope=(dev(cos[:, :32].contiguous()), dev(sin[:, :32].contiguous()), n, 2 * D))
+        H = D // 64
+        qkv = lin.view(B, n, 3, H, 64)
+        q, k, v = (qkv[:, :, i].transpose(1, 2) for i in range(3))
+        q, k = VO.rotate_half_apply(q, cos, sin), VO.rotate_half_apply(k, cos, sin)
+        ref = torch.stack([t.transpose(1, 2) for t in (q, k, v)], dim=2).reshape(M, N)
+    else:
+        epi, fn = (L.VF_EPI_GELU_TANH_BF16, VO.gelu_tanh) if mode == "tanh" else (L.VF_EPI_GELU_ERF_BF16, VO.gelu_erf)
+        L.gemm(xb, dev(wf), epi, out, bias=dev(bfold), ln_in=(rows, dev(cs)))
+        ref = fn(lin)
+    check_close(out, ref, tol=6e-3, what=f"folded layernorm -> {mode}")
+
+
+def test_gemm_folded_layernorm_rejects_bad_arguments(L):
+    M, N, K = 256, 768, 768
+    a, w = dev(bf(rnd(M, K, seed=80))), dev(bf(rnd(N, K, seed=81)))
+    out = torch.zeros((M, N), dtype=torch.bfloat16, device="cuda")
+    rows, cs = torch.zeros((M, 2), device="cuda"), torch.zeros(N, device="cuda")
+    with pytest.raises(L.VFuseError):                         # epilogue without a folded-LN form
+        L.gemm(a, w, L.VF_EPI_BIAS_BF16, out, ln_in=(rows, cs))
+    xf = torch.zeros((M, N), device="cuda")
+    with pytest.raises(L.VFuseError):                         # producer needs the residual epilogue
+        L.gemm(a, w, L.VF_EPI_BIAS_F32, xf, ln_out=(out, torch.zeros((N // 32, M, 2), device="cuda")))
+
+
 # ------------------------------------------------------------------------------------------------
 # patch embedding (im2col-free TMA gather)
 # ------------------------------------------------------------------------------------------------
@@ -147,6 +222,27 @@ def test_patch_embed3d(L, B, T, H, W, D):
     L.patch_embed(dev(x), dev(w.reshape(D, -1).contiguous()), dev(b), dev(pos), out, P, tp, S, 0)
     ref = VO.patch_embed3d(x.float(), w.float(), b) + pos[:n].repeat(T // tp, 1)[None]
     check_close(out.view(B, S, D), ref, tol=2e-3, what=f"patch_embed3d {B}x{T}x{H}x{W}")
+
+
+def test_patch_embed3d_folded_layernorm_outputs(L):
+    """vf_patch_embed_ln: bf16 copy + partial row sums next to the fp32 rows (ragged tile rectangles included)."""
+    B, T, H, W, D, P, tp = 2, 2, 160, 48, 128, 16, 2
+    x = bf(rnd(B, 3, T, H, W, seed=20))
+    w = bf(rnd(D, 3, tp, P, P, seed=21, scale=0.03))
+    b = rnd(D, seed=22)
+    n = (H // P) * (W // P)
+    pos = rnd(n, D, seed=23)
+    S = (T // tp) * n
+    out = torch.full((B * S, D), float("nan"), device="cuda")
+    xb = torch.zeros((B * S, D), dtype=torch.bfloat16, device="cuda")
+    stat = torch.full((D // 32, B * S, 2), float("nan"), device="cuda")
+    L.patch_embed(dev(x), dev(w.reshape(D, -1).contiguous()), dev(b), dev(pos), out, P, tp, S, 0, ln_out=(xb, stat))
+    ref = VO.patch_embed3d(x.float(), w.float(), b) + pos[:n].repeat(T // tp, 1)[None]
+    check_close(out.view(B, S, D), ref, tol=2e-3, what="patch_embed3d (ln outputs)")
+    assert torch.equal(xb.cpu(), bf(out.cpu()))
+    blocks = out.cpu().view(B * S, D // 32, 32)
+    torch.testing.assert_close(stat[:, :, 0].cpu().t(), blocks.sum(-1), rtol=1e-5, atol=1e-4)
+    torch.testing.assert_close(stat[:, :, 1].cpu().t(), (blocks * blocks).sum(-1), rtol=1e-5, atol=1e-4)
 
 
 def test_patch_embed2d_with_cls_rows(L):

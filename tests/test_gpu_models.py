@@ -128,11 +128,14 @@ def _random_qwen_sd(model, seed=123):
     return sd
 
 
-@pytest.mark.parametrize("px,T,B", [(448, 2, 2), (224, 4, 1)])
-def test_qwen_tower_full_size_vs_oracle(px, T, B):
-    """cfg-2 / cfg-4 shapes with the batch reduced to what the CPU oracle finishes in seconds."""
+@pytest.mark.parametrize("px,T,B,ln_fuse", [(448, 2, 2, None), (224, 4, 1, None), (448, 2, 2, "0"), (448, 2, 2, "2")])
+def test_qwen_tower_full_size_vs_oracle(px, T, B, ln_fuse, monkeypatch):
+    """cfg-2 / cfg-4 shapes with the batch reduced to what the CPU oracle finishes in seconds. ln_fuse: every
+    LayerNorm placement (stand-alone kernels / norm1 folded into the GEMMs (default) / norm1 and norm2 folded)."""
     from llm_quest_b200.qwen.qwen3_5.qwen3_5_vision_model import Qwen3_5VisionModel
 
+    if ln_fuse is not None:
+        monkeypatch.setenv("VF_LN_FUSE", ln_fuse)
     cfg = qwen_cfg(px)
     torch.manual_seed(123)
     m = Qwen3_5VisionModel(cfg).eval()
@@ -145,7 +148,7 @@ def test_qwen_tower_full_size_vs_oracle(px, T, B):
         ref = VO.qwen_vision_forward(sd, cfg, pixels)
         out = m.cuda()(pixels.cuda())
     assert out.shape == (B, (T // 2) * (px // 32) ** 2, 1024)
-    check_close(out, ref, f"Qwen3-ViT tower {px}px T={T} vs fp32 oracle")
+    check_close(out, ref, f"Qwen3-ViT tower {px}px T={T} ln_fuse={ln_fuse} vs fp32 oracle")
 
 
 def test_vit_b16_vs_oracle():

@@ -78,6 +78,22 @@ def main():
     ms = timeit(fn)
     print(f"lin2_res  M={M} N=768  K=3072: {ms*1e3:7.1f} us {2*M*F*D/ms/1e9:7.1f} TF err={e_:.2e}", flush=True)
 
+    # --- folded LayerNorm: the same four GEMMs with the producer / consumer epilogue extras
+    xb = torch.empty(M, D, device="cuda", dtype=torch.bfloat16)
+    stat = torch.empty(D // 32, M, 2, device="cuda")
+    rs = torch.empty(M, 2, device="cuda")
+    cs3, csq = rnd(F), rnd(3 * D)
+    for name, fn, fl in [
+        ("proj_res+ln_out ", lambda: L.gemm(a, w2, L.VF_EPI_BIAS_RES_F32, x, bias=b2, res=x, ln_out=(xb, stat)), 2 * M * D * D),
+        ("lin2_res+ln_out ", lambda: L.gemm(gout, w4, L.VF_EPI_BIAS_RES_F32, x, bias=b4, res=x, ln_out=(xb, stat)), 2 * M * F * D),
+        ("ln_row_stats    ", lambda: L.ln_row_stats(stat, D, 1e-6, rs), 0),
+        ("lin1_gelu+ln_in ", lambda: L.gemm(a, w3, L.VF_EPI_GELU_TANH_BF16, gout, bias=b3, ln_in=(rs, cs3)), 2 * M * F * D),
+        ("qkv_rope+ln_in  ", lambda: L.gemm(a, w, L.VF_EPI_QKV_ROPE_BF16, out, bias=b, rope=(cos, sin, n, 2 * D), ln_in=(rs, csq)), 2 * M * 3 * D * D),
+    ]:
+        x.copy_(x0)
+        ms = timeit(fn)
+        print(f"{name} M={M}: {ms*1e3:7.1f} us {fl/ms/1e9:7.1f} TF", flush=True)
+
     # --- cuBLAS reference points (plain bf16 GEMMs, no epilogue) for the same shapes
     for (N, K, name) in [(2304, 768, "cublas qkv "), (768, 768, "cublas proj"), (3072, 768, "cublas lin1"), (768, 3072, "cublas lin2")]:
         aa = rnd(M, K).bfloat16(); ww = rnd(N, K, sc=0.03).bfloat16()
