@@ -291,8 +291,11 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
       return v;
     };
 
-    auto write_staged2 = [&](uint32_t st, int rr, float a, float b) {   // first 8 bytes of the slot read_staged(rr) returns
-      asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(st + rr * 128 + ((cl ^ (rr & 7)) << 4)), "f"(a), "f"(b)
+    // 8 bytes of the slot read_staged(rr) returns: the upper half for rows 8..15 and 24..31, so that the per-row read-back
+    // (lane = row) meets 2-way instead of 4-way bank conflicts
+    auto write_staged2 = [&](uint32_t st, int rr, float a, float b) {
+      asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(st + rr * 128 + ((cl ^ (rr & 7)) << 4) + (rr & 8)), "f"(a),
+                   "f"(b)
                    : "memory");
     };
 
@@ -584,7 +587,7 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
                   float a_, b_;
                   asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];"
                                : "=f"(a_), "=f"(b_)
-                               : "r"(stA + lane * 128 + ((k ^ (lane & 7)) << 4))
+                               : "r"(stA + lane * 128 + ((k ^ (lane & 7)) << 4) + (lane & 8))
                                : "memory");
                   s_ += a_; q_ += b_;
                 }

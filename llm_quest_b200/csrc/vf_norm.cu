@@ -130,22 +130,36 @@ __global__ void vit_cls_pos_kernel(const float* __restrict__ cls, const float* _
     out[static_cast<long long>(b) * rows_per_sample * D + d] = cls[d] + pos[d];
 }
 
+// One block = 32 rows x 8 groups of partials: thread (g, r) adds the partials j = g, g+8, ... of row r (coalesced 256-byte
+// rows of float2), the 8 group sums meet in shared memory and warp 0 adds them in fixed order.
 __global__ void __launch_bounds__(256) ln_row_stats_kernel(const float2* __restrict__ part, int parts, long long ld,
                                                            long long rows, float inv_d, float eps,
                                                            float2* __restrict__ out) {
+  __shared__ float2 acc[8][32];
   pdl_wait();
   pdl_launch_dependents();
-  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= rows) return;
+  const int g = threadIdx.x >> 5, l = threadIdx.x & 31;
+  const long long r = (long long)blockIdx.x * 32 + l;
   float s = 0.f, q = 0.f;
-#pragma unroll 8
-  for (int j = 0; j < parts; ++j) {
-    const float2 t = __ldg(part + (long long)j * ld + r);
-    s += t.x;
-    q += t.y;
+  if (r < rows) {
+#pragma unroll 4
+    for (int j = g; j < parts; j += 8) {
+      const float2 t = __ldg(part + (long long)j * ld + r);
+      s += t.x;
+      q += t.y;
+    }
   }
-  const float mu = s * inv_d;
-  out[r] = make_float2(mu, rsqrtf(fmaxf(fmaf(-mu, mu, q * inv_d), 0.f) + eps));
+  acc[g][l] = make_float2(s, q);
+  __syncthreads();
+  if (g == 0 && r < rows) {
+#pragma unroll
+    for (int k = 1; k < 8; ++k) {
+      s += acc[k][l].x;
+      q += acc[k][l].y;
+    }
+    const float mu = s * inv_d;
+    out[r] = make_float2(mu, rsqrtf(fmaxf(fmaf(-mu, mu, q * inv_d), 0.f) + eps));
+  }
 }
 
 }  // namespace vf
@@ -157,7 +171,7 @@ extern "C" int vf_ln_row_stats(const void* partials, int32_t parts, int64_t ld, 
   VF_REQUIRE(partials && out && parts > 0 && rows > 0 && D > 0 && ld >= rows, VF_ERR_ARG, "vf_ln_row_stats: bad arguments");
   VF_REQUIRE((reinterpret_cast<uintptr_t>(partials) & 7) == 0 && (reinterpret_cast<uintptr_t>(out) & 7) == 0, VF_ERR_ALIGN,
              "vf_ln_row_stats: pointers must be 8-byte aligned");
-  const unsigned grid = static_cast<unsigned>((rows + 255) / 256);
+  const unsigned grid = static_cast<unsigned>((rows + 31) / 32);
   VF_CUDA(launch_pdl(ln_row_stats_kernel, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream), 1,
                      static_cast<const float2*>(partials), (int)parts, (long long)ld, (long long)rows,
                      1.0f / static_cast<float>(D), eps, static_cast<float2*>(out)));
