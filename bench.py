@@ -24,6 +24,7 @@ from __future__ import annotations
 
 import argparse
 import json
+import re
 import os
 import subprocess
 import sys
@@ -65,7 +66,10 @@ def measured_peaks():
 
 def measured_traffic():
     """DRAM bytes per launch of the dominant kernel family from the committed ncu --set full capture."""
-    files = sorted((ROOT / "profiles").glob("*_traffic.json"))
+    def order(f):   # r01_v10 after r01_v7: numeric, not lexicographic
+        return [int(n) for n in re.findall(r"\d+", f.name)]
+
+    files = sorted((ROOT / "profiles").glob("*_traffic.json"), key=order)
     if not files:
         return None, None
     d = json.loads(files[-1].read_text())
