@@ -55,6 +55,7 @@ struct GemmParams {
   int rope_cols;
   const int* dst_rows;
   int vec_ok;          // out (and res) rows are 16-byte aligned: 128-bit stores allowed
+  int res_tma;         // residual epilogue through TMA (identity row map, N % 32 == 0): see the RING path
   int n_peers;         // > 0: fused all-gather, every element goes to peer[0..n_peers) (NVLink peer memory) instead of out
   char* peer[8];
   // patch-embedding mode
@@ -77,16 +78,28 @@ struct GemmParams {
 // CG = 1: one CTA per 128 x BN tile. CG = 2: a CTA pair (cta_group::2) per 256 x BN tile — each CTA stages
 // its own 128 A rows and HALF of the W tile, so a k-block costs 32 KB of L2->SM traffic per SM instead of
 // 48 KB (the 1-CTA kernel was capped by exactly that traffic, ~70 % tensor-pipe active) and six stages fit.
-template <int BN, int CG>
+// RING (the fp32 residual epilogue of the CTA-pair kernel): four stages, and instead of the 32 KB of staging blocks
+// every epilogue warp owns two 32x32 fp32 slots (TMA-loaded residual block, updated in place, TMA-stored) plus one
+// 32x32 bf16 slot (the folded-LayerNorm copy of the row).
+template <int BN, int CG, bool RING = false>
 struct SmemLayout {
-  static constexpr int STAGES = CG == 2 ? 6 : 4;
+  static constexpr int STAGES = RING ? 4 : (CG == 2 ? 6 : 4);
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = (BN / CG) * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
-  static constexpr int EPI_OFF = BAR_OFF + 256;            // 32 KB of 32x32 fp32 staging blocks for the epilogue warps
-  static constexpr int TOTAL = EPI_OFF + 4 * 8192 + 1024;  // + alignment slack
+  static constexpr int EPI_OFF = BAR_OFF + (RING ? 1024 : 256);   // ring slots need 1024-byte alignment (128 B swizzle)
+  static constexpr int RING_WARP_BYTES = 2 * 4096 + 2048;
+  static constexpr int EPI_BYTES = RING ? 8 * RING_WARP_BYTES : 4 * 8192;   // else: 32x32 fp32 staging blocks
+  static constexpr int TOTAL = EPI_OFF + EPI_BYTES + 1024;  // + alignment slack
 };
+
+struct EpiMaps {   // tensor maps of the TMA residual epilogue (32x32 boxes): residual in, fp32 out, bf16 copy out
+  CUtensorMap res, out, xb;
+};
+
+template <int EPI, bool PATCH, int CG>
+constexpr bool kRing = (EPI == VF_EPI_BIAS_RES_F32 && !PATCH && CG == 2);
 
 __device__ __forceinline__ void wait_or_trap(uint64_t* bar, uint32_t parity) {
   // Bounded wait: a protocol bug becomes a trap (CUDA error) instead of a hung GPU.
@@ -127,9 +140,10 @@ __device__ __forceinline__ float gelu_erf_f(float x) {
 template <int EPI, int BN, bool PATCH, int CG>
 __global__ void __launch_bounds__(EpiCfg<EPI>::THREADS, 1)
 gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
-            const __grid_constant__ CUtensorMap tmB) {
+            const __grid_constant__ CUtensorMap tmB, const __grid_constant__ EpiMaps em) {
   static_assert(CG == 1 || (CG == 2 && BN == 256 && !PATCH), "CTA pairs: 256-wide tiles, plain A operand");
-  using L = SmemLayout<BN, CG>;
+  constexpr bool RING = kRing<EPI, PATCH, CG>;
+  using L = SmemLayout<BN, CG, RING>;
   constexpr int STAGES = L::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -138,6 +152,7 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
   uint64_t* tfull_bar = empty_bar + STAGES;   // [2]
   uint64_t* tempty_bar = tfull_bar + 2;       // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  [[maybe_unused]] uint64_t* rfull_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF + 256);   // RING: [8 warps][2 slots]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -156,6 +171,11 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
       mbar_init(&tempty_bar[a], EpiCfg<EPI>::WARPS * CG);  // one arrival per epilogue warp (of both CTAs)
+    }
+    if constexpr (RING) {
+      tma_prefetch_desc(&em.res);
+      tma_prefetch_desc(&em.out);
+      for (int i = 0; i < 16; ++i) mbar_init(&rfull_bar[i], 1);
     }
     fence_barrier_init();
   }
@@ -318,7 +338,107 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
     };
     prefetch_res(tile0);
 
-    for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+    // ------------------------------------------------------------------ residual epilogue through TMA (RING)
+    // The staged epilogue moves every fp32 element through the SM's load/store unit four times (stage, read back,
+    // residual load, store): 512 KB per 128x256 tile, more LSU time than the K=768 main loop takes — the proj GEMM
+    // was bound by exactly that, not by DRAM (a residual that always hits L1 cost the same +25 us). Here TMA brings
+    // the 32x32 residual block into a swizzled slot, every thread adds its accumulator ROW in place (thread = row, so
+    // the folded-LayerNorm row sums are thread-local: no shuffles, no second pass) and TMA stores the slot: 256 KB of
+    // LSU traffic per tile, no transposition, no global load/store instructions at all.
+    bool ring_done = false;
+    if constexpr (RING) {
+      if (p.res_tma) {
+        ring_done = true;
+        const int ew = warp - 2;
+        uint8_t* ring = smem + L::EPI_OFF + ew * L::RING_WARP_BYTES;
+        const uint32_t ring_u = smem_u32(ring);
+        uint64_t* rf = rfull_bar + ew * 2;
+        const bool ln_out = p.ln_xb != nullptr;
+        auto issue_load = [&](int tile, int c, int slot) {   // lane 0
+          const int col = (tile % p.num_n_blk) * BN + chalf * COLS_PER_WARP + c * 32;
+          const int row = ((tile / p.num_n_blk) * CG + rank) * BM + quarter * 32;
+          mbar_expect_tx(&rf[slot], 4096);
+          tma_load_2d(ring + slot * 4096, &em.res, &rf[slot], col, row);
+        };
+        uint32_t bc = 0;   // blocks done by this warp: slot = bc & 1, barrier parity = (bc >> 1) & 1
+        if (lane == 0 && tile0 < num_tiles) issue_load(tile0, 0, 0);
+        for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+          const int col0 = (tile % p.num_n_blk) * BN + chalf * COLS_PER_WARP;
+          const int row0 = ((tile / p.num_n_blk) * CG + rank) * BM + quarter * 32;
+          prefetch_res(tile + tile_step);
+          const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + chalf * COLS_PER_WARP;
+#pragma unroll 1
+          for (int c = 0; c < COLS_PER_WARP / 32; ++c) {
+            const int slot = bc & 1;
+            const int col = col0 + c * 32;
+            if (lane == 0) {
+              // every earlier store has left shared memory: the other fp32 slot and the bf16 slot may be rewritten
+              tma_store_wait_read<0>();
+              const bool last = c == COLS_PER_WARP / 32 - 1;
+              const int nt = last ? tile + tile_step : tile;
+              if (nt < num_tiles) issue_load(nt, last ? 0 : c + 1, slot ^ 1);
+            }
+            __syncwarp();
+            if (c == 0) {
+              wait_or_trap(&tfull_bar[acc], acc_phase);
+              tc_fence_after();
+            }
+            uint32_t r[32];
+            tmem_ld_x32(t_row + c * 32, r);
+            wait_or_trap(&rf[slot], (bc >> 1) & 1);
+            tmem_ld_wait();
+            if (c == COLS_PER_WARP / 32 - 1) {   // all tcgen05.ld of this warp for the tile are complete
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive_leader(&tempty_bar[acc]);
+            }
+            const uint32_t rowb = ring_u + slot * 4096 + lane * 128;
+            const uint32_t xrow = ring_u + 8192 + lane * 64;
+            float s_ = 0.f, q_ = 0.f;
+            uint32_t xw[4];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const uint32_t a = rowb + ((j ^ (lane & 7)) << 4);
+              float4 x;
+              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(a) : "memory");
+              float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (p.bias) bv = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4 * j));   // uniform: one broadcast wavefront
+              x.x += __uint_as_float(r[4 * j]) + bv.x;
+              x.y += __uint_as_float(r[4 * j + 1]) + bv.y;
+              x.z += __uint_as_float(r[4 * j + 2]) + bv.z;
+              x.w += __uint_as_float(r[4 * j + 3]) + bv.w;
+              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(x.x), "f"(x.y), "f"(x.z), "f"(x.w) : "memory");
+              if (ln_out) {
+                // same association as the staged epilogue (4-column shares added in column order): a row's statistics
+                // must not depend on which of the two paths its batch size selects
+                s_ += (x.x + x.y) + (x.z + x.w);
+                q_ += fmaf(x.x, x.x, fmaf(x.y, x.y, fmaf(x.z, x.z, x.w * x.w)));
+                xw[(j & 1) * 2] = pack_bf16(x.x, x.y);
+                xw[(j & 1) * 2 + 1] = pack_bf16(x.z, x.w);
+                if (j & 1)   // 64-byte rows, 64 B swizzle: chunk ^= (row >> 1) & 3
+                  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(xrow + (((j >> 1) ^ ((lane >> 1) & 3)) << 4)),
+                               "r"(xw[0]), "r"(xw[1]), "r"(xw[2]), "r"(xw[3])
+                               : "memory");
+              }
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&em.out, ring + slot * 4096, col, row0);
+              if (ln_out) tma_store_2d(&em.xb, ring + 8192, col, row0);
+              tma_store_commit();
+            }
+            if (ln_out && row0 + lane < p.M)
+              p.ln_stat_out[(long long)(col >> 5) * p.ln_stat_ld + row0 + lane] = make_float2(s_, q_);
+            ++bc;
+          }
+          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+        if (lane == 0) tma_store_wait<0>();
+      }
+    }
+
+    for (int tile = ring_done ? num_tiles : tile0; tile < num_tiles; tile += tile_step) {
       const int n_blk = tile % p.num_n_blk;
       const int m_blk = (tile / p.num_n_blk) * CG + rank;
       const int col0 = n_blk * BN;
@@ -643,8 +763,10 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
 // ------------------------------------------------------------------------------------------------
 template <int EPI, int BN, bool PATCH = false, int CG = 1>
 static int launch_gemm(const GemmParams& p, const CUtensorMap& tmA, const CUtensorMap& tmB,
-                       cudaStream_t stream) {
-  using L = SmemLayout<BN, CG>;
+                       cudaStream_t stream, const EpiMaps* em_in = nullptr) {
+  using L = SmemLayout<BN, CG, kRing<EPI, PATCH, CG>>;
+  static const EpiMaps no_maps{};
+  const EpiMaps& em = em_in ? *em_in : no_maps;
   static bool configured = false;
   auto kfn = gemm_kernel<EPI, BN, PATCH, CG>;
   if (!configured) {
@@ -656,7 +778,7 @@ static int launch_gemm(const GemmParams& p, const CUtensorMap& tmA, const CUtens
   const int tiles = ((p.num_m_blk + CG - 1) / CG) * p.num_n_blk;
   const int slots = sms / CG;                       // persistent: one CTA (pair) per SM (pair)
   const int grid = (tiles < slots ? tiles : slots) * CG;
-  VF_CUDA(launch_pdl(kfn, dim3(grid), dim3(EpiCfg<EPI>::THREADS), L::TOTAL, stream, CG, p, tmA, tmB));
+  VF_CUDA(launch_pdl(kfn, dim3(grid), dim3(EpiCfg<EPI>::THREADS), L::TOTAL, stream, CG, p, tmA, tmB, em));
   count_launch();
   VF_CUDA(cudaGetLastError());
   return VF_OK;
@@ -664,11 +786,11 @@ static int launch_gemm(const GemmParams& p, const CUtensorMap& tmA, const CUtens
 
 template <int BN, int CG>
 static int dispatch_epi(int mode, const GemmParams& p, const CUtensorMap& a, const CUtensorMap& b,
-                        cudaStream_t s) {
+                        cudaStream_t s, const EpiMaps* em = nullptr) {
   switch (mode) {
     case VF_EPI_BIAS_BF16: return launch_gemm<VF_EPI_BIAS_BF16, BN, false, CG>(p, a, b, s);
     case VF_EPI_BIAS_F32: return launch_gemm<VF_EPI_BIAS_F32, BN, false, CG>(p, a, b, s);
-    case VF_EPI_BIAS_RES_F32: return launch_gemm<VF_EPI_BIAS_RES_F32, BN, false, CG>(p, a, b, s);
+    case VF_EPI_BIAS_RES_F32: return launch_gemm<VF_EPI_BIAS_RES_F32, BN, false, CG>(p, a, b, s, em);
     case VF_EPI_GELU_TANH_BF16: return launch_gemm<VF_EPI_GELU_TANH_BF16, BN, false, CG>(p, a, b, s);
     case VF_EPI_GELU_ERF_BF16: return launch_gemm<VF_EPI_GELU_ERF_BF16, BN, false, CG>(p, a, b, s);
     case VF_EPI_QKV_ROPE_BF16: return launch_gemm<VF_EPI_QKV_ROPE_BF16, BN, false, CG>(p, a, b, s);
@@ -799,7 +921,29 @@ extern "C" int vf_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t l
     if (e) return e;
   }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (cg == 2) return dispatch_epi<256, 2>(ep->mode, p, tmA, tmB, s);
+  // TMA residual epilogue (VF_RES_TMA=0: the staged register epilogue, development A/B switch)
+  static int res_tma_env = -1;
+  if (res_tma_env < 0) {
+    const char* e_ = getenv("VF_RES_TMA");
+    res_tma_env = e_ ? atoi(e_) : 1;
+  }
+  EpiMaps em{};
+  if (cg == 2 && ep->mode == VF_EPI_BIAS_RES_F32 && ep->grp_rows <= 0 && vec_ok && (N % 32) == 0 && res_tma_env &&
+      (!p.ln_xb || ((p.ln_ldxb % 8) == 0 && (reinterpret_cast<uintptr_t>(p.ln_xb) & 15) == 0))) {
+    uint64_t dims[2] = {(uint64_t)N, (uint64_t)M};
+    uint32_t box[2] = {32, 32};
+    uint64_t sr[1] = {(uint64_t)ep->ldr * 4}, so[1] = {(uint64_t)ep->ldo * 4}, sx[1] = {(uint64_t)p.ln_ldxb * 2};
+    int e = encode_tmap(&em.res, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, ep->res, dims, sr, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (e) return e;
+    e = encode_tmap(&em.out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, ep->out, dims, so, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (e) return e;
+    if (p.ln_xb) {
+      e = encode_tmap(&em.xb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, p.ln_xb, dims, sx, box, CU_TENSOR_MAP_SWIZZLE_64B);
+      if (e) return e;
+    }
+    p.res_tma = 1;
+  }
+  if (cg == 2) return dispatch_epi<256, 2>(ep->mode, p, tmA, tmB, s, &em);
   return bn == 256 ? dispatch_epi<256, 1>(ep->mode, p, tmA, tmB, s)
                    : dispatch_epi<128, 1>(ep->mode, p, tmA, tmB, s);
 }

@@ -155,6 +155,39 @@ def test_gemm_folded_layernorm_producer(L, M):
     torch.testing.assert_close(stat[:, :, 1].cpu().t(), (blocks * blocks).sum(-1), rtol=1e-5, atol=1e-4)
 
 
+@pytest.mark.parametrize("with_ln", [False, True])
+def test_gemm_residual_tma_epilogue_matches_staged_epilogue_bit_exact(L, with_ln):
+    """Large M takes the CTA-pair kernel whose residual epilogue runs through TMA (32x32 blocks updated in place in
+    shared memory); small M takes the single-CTA kernel with the staged register epilogue. Same rows, same bits —
+    fp32 rows, bf16 copy and LayerNorm partial sums — and a ragged last row block (4500 = 35 * 128 + 20)."""
+    M, N, K = 4500, 768, 320
+    a, w, b = dev(bf(rnd(M, K, seed=90))), dev(bf(rnd(N, K, seed=91, scale=0.05))), dev(rnd(N, seed=92))
+    res = rnd(M, N, seed=93) + 0.25
+    ref = a.float().cpu() @ w.float().cpu().t() + b.cpu() + res
+
+    def run(rows):
+        x = dev(res[rows].clone())
+        n = x.shape[0]
+        xb = torch.zeros((n, N), dtype=torch.bfloat16, device="cuda")
+        stat = torch.full((N // 32, n, 2), float("nan"), device="cuda")
+        L.gemm(a[rows], w, L.VF_EPI_BIAS_RES_F32, x, bias=b, res=x, ln_out=(xb, stat) if with_ln else None)
+        return x.cpu(), xb.cpu(), stat.cpu()
+
+    big = run(slice(0, M))
+    check_close(big[0], ref, tol=2e-3, what="TMA residual epilogue vs fp32 oracle")
+    for lo in (0, 2048, 4096):
+        hi = min(lo + 1024, M)
+        small = run(slice(lo, hi))                       # 8 row blocks: 128-wide tiles, staged epilogue
+        assert torch.equal(big[0][lo:hi], small[0]), f"fp32 rows differ between the two epilogues at {lo}"
+        if with_ln:
+            assert torch.equal(big[1][lo:hi], small[1]), "bf16 copies differ"
+            assert torch.equal(big[2][:, lo:hi], small[2]), "LayerNorm partial sums differ"
+    if with_ln:
+        assert torch.equal(big[1], bf(big[0]))
+        blocks = big[0].view(M, N // 32, 32)
+        torch.testing.assert_close(big[2][:, :, 0].t(), blocks.sum(-1), rtol=1e-5, atol=1e-4)
+
+
 @pytest.mark.parametrize("mode", ["tanh", "erf", "qkv"])
 def test_gemm_folded_layernorm_consumer(L, mode):
     """producer -> consumer chain equals LayerNorm followed by the plain GEMM (oracle: fp32 LN + Linear)."""
