@@ -79,8 +79,8 @@ struct GemmParams {
 // its own 128 A rows and HALF of the W tile, so a k-block costs 32 KB of L2->SM traffic per SM instead of
 // 48 KB (the 1-CTA kernel was capped by exactly that traffic, ~70 % tensor-pipe active) and six stages fit.
 // RING (the fp32 residual epilogue of the CTA-pair kernel): four stages, and instead of the 32 KB of staging blocks
-// every epilogue warp owns two 32x32 fp32 slots (TMA-loaded residual block, updated in place, TMA-stored) plus one
-// 32x32 bf16 slot (the folded-LayerNorm copy of the row).
+// every epilogue warp owns 12 KB: three 32x32 fp32 slots (TMA-loaded residual block, updated in place, TMA-stored), or
+// two of them plus one 32x32 bf16 slot when the folded-LayerNorm copy of the rows is written as well.
 template <int BN, int CG, bool RING = false>
 struct SmemLayout {
   static constexpr int STAGES = RING ? 4 : (CG == 2 ? 6 : 4);
@@ -89,7 +89,7 @@ struct SmemLayout {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
   static constexpr int EPI_OFF = BAR_OFF + (RING ? 1024 : 256);   // ring slots need 1024-byte alignment (128 B swizzle)
-  static constexpr int RING_WARP_BYTES = 2 * 4096 + 2048;
+  static constexpr int RING_WARP_BYTES = 3 * 4096;   // three fp32 slots, or two + the bf16 slot (folded-LN producer)
   static constexpr int EPI_BYTES = RING ? 8 * RING_WARP_BYTES : 4 * 8192;   // else: 32x32 fp32 staging blocks
   static constexpr int TOTAL = EPI_OFF + EPI_BYTES + 1024;  // + alignment slack
 };
@@ -152,7 +152,7 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
   uint64_t* tfull_bar = empty_bar + STAGES;   // [2]
   uint64_t* tempty_bar = tfull_bar + 2;       // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  [[maybe_unused]] uint64_t* rfull_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF + 256);   // RING: [8 warps][2 slots]
+  [[maybe_unused]] uint64_t* rfull_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF + 256);   // RING: [8 warps][3 slots]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -175,7 +175,7 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
     if constexpr (RING) {
       tma_prefetch_desc(&em.res);
       tma_prefetch_desc(&em.out);
-      for (int i = 0; i < 16; ++i) mbar_init(&rfull_bar[i], 1);
+      for (int i = 0; i < 24; ++i) mbar_init(&rfull_bar[i], 1);
     }
     fence_barrier_init();
   }
@@ -352,16 +352,24 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
         const int ew = warp - 2;
         uint8_t* ring = smem + L::EPI_OFF + ew * L::RING_WARP_BYTES;
         const uint32_t ring_u = smem_u32(ring);
-        uint64_t* rf = rfull_bar + ew * 2;
+        uint64_t* rf = rfull_bar + ew * 3;
         const bool ln_out = p.ln_xb != nullptr;
-        auto issue_load = [&](int tile, int c, int slot) {   // lane 0
-          const int col = (tile % p.num_n_blk) * BN + chalf * COLS_PER_WARP + c * 32;
-          const int row = ((tile / p.num_n_blk) * CG + rank) * BM + quarter * 32;
-          mbar_expect_tx(&rf[slot], 4096);
-          tma_load_2d(ring + slot * 4096, &em.res, &rf[slot], col, row);
+        const int R = ln_out ? 2 : 3;                        // fp32 slots (the third one is the bf16 slot with ln_out)
+        // load cursor: block (nl_tile, nl_c) goes into slot nl_slot next (lane 0)
+        int nl_tile = tile0, nl_c = 0, nl_slot = 0;
+        auto issue_load = [&]() {
+          if (nl_tile >= num_tiles) return;
+          const int col = (nl_tile % p.num_n_blk) * BN + chalf * COLS_PER_WARP + nl_c * 32;
+          const int row = ((nl_tile / p.num_n_blk) * CG + rank) * BM + quarter * 32;
+          mbar_expect_tx(&rf[nl_slot], 4096);
+          tma_load_2d(ring + nl_slot * 4096, &em.res, &rf[nl_slot], col, row);
+          if (++nl_c == COLS_PER_WARP / 32) { nl_c = 0; nl_tile += tile_step; }
+          if (++nl_slot == R) nl_slot = 0;
         };
-        uint32_t bc = 0;   // blocks done by this warp: slot = bc & 1, barrier parity = (bc >> 1) & 1
-        if (lane == 0 && tile0 < num_tiles) issue_load(tile0, 0, 0);
+        int slot = 0;
+        uint32_t ph = 0;   // parity of rf[slot] for the block being processed
+        if (lane == 0)
+          for (int i = 0; i < R - 1; ++i) issue_load();      // R-1 blocks in flight ahead of the one being processed
         for (int tile = tile0; tile < num_tiles; tile += tile_step) {
           const int col0 = (tile % p.num_n_blk) * BN + chalf * COLS_PER_WARP;
           const int row0 = ((tile / p.num_n_blk) * CG + rank) * BM + quarter * 32;
@@ -369,14 +377,12 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
           const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + chalf * COLS_PER_WARP;
 #pragma unroll 1
           for (int c = 0; c < COLS_PER_WARP / 32; ++c) {
-            const int slot = bc & 1;
             const int col = col0 + c * 32;
             if (lane == 0) {
-              // every earlier store has left shared memory: the other fp32 slot and the bf16 slot may be rewritten
+              // every earlier store has left shared memory: the slot of the previous block (and the bf16 slot) may be
+              // rewritten, so the load that runs R-1 blocks ahead goes into it
               tma_store_wait_read<0>();
-              const bool last = c == COLS_PER_WARP / 32 - 1;
-              const int nt = last ? tile + tile_step : tile;
-              if (nt < num_tiles) issue_load(nt, last ? 0 : c + 1, slot ^ 1);
+              issue_load();
             }
             __syncwarp();
             if (c == 0) {
@@ -385,41 +391,53 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
             }
             uint32_t r[32];
             tmem_ld_x32(t_row + c * 32, r);
-            wait_or_trap(&rf[slot], (bc >> 1) & 1);
+            // the 32 bias values of the block (uniform addresses: one broadcast wavefront per load), requested before
+            // the waits; loads, adds and stores below are batched so that nothing waits on a single round trip
+            float4 bv[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              bv[j] = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + col + 4 * j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            wait_or_trap(&rf[slot], ph);
+            const uint32_t rowb = ring_u + slot * 4096 + lane * 128;
+            const uint32_t xrow = ring_u + 8192 + lane * 64;
+            float4 x[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                           : "=f"(x[j].x), "=f"(x[j].y), "=f"(x[j].z), "=f"(x[j].w)
+                           : "r"(rowb + ((j ^ (lane & 7)) << 4))
+                           : "memory");
             tmem_ld_wait();
             if (c == COLS_PER_WARP / 32 - 1) {   // all tcgen05.ld of this warp for the tile are complete
               tc_fence_before();
               __syncwarp();
               if (lane == 0) mbar_arrive_leader(&tempty_bar[acc]);
             }
-            const uint32_t rowb = ring_u + slot * 4096 + lane * 128;
-            const uint32_t xrow = ring_u + 8192 + lane * 64;
             float s_ = 0.f, q_ = 0.f;
-            uint32_t xw[4];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const uint32_t a = rowb + ((j ^ (lane & 7)) << 4);
-              float4 x;
-              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(a) : "memory");
-              float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (p.bias) bv = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4 * j));   // uniform: one broadcast wavefront
-              x.x += __uint_as_float(r[4 * j]) + bv.x;
-              x.y += __uint_as_float(r[4 * j + 1]) + bv.y;
-              x.z += __uint_as_float(r[4 * j + 2]) + bv.z;
-              x.w += __uint_as_float(r[4 * j + 3]) + bv.w;
-              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(x.x), "f"(x.y), "f"(x.z), "f"(x.w) : "memory");
-              if (ln_out) {
+              x[j].x += __uint_as_float(r[4 * j]) + bv[j].x;
+              x[j].y += __uint_as_float(r[4 * j + 1]) + bv[j].y;
+              x[j].z += __uint_as_float(r[4 * j + 2]) + bv[j].z;
+              x[j].w += __uint_as_float(r[4 * j + 3]) + bv[j].w;
+              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(rowb + ((j ^ (lane & 7)) << 4)), "f"(x[j].x),
+                           "f"(x[j].y), "f"(x[j].z), "f"(x[j].w)
+                           : "memory");
+            }
+            if (ln_out) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
                 // same association as the staged epilogue (4-column shares added in column order): a row's statistics
                 // must not depend on which of the two paths its batch size selects
-                s_ += (x.x + x.y) + (x.z + x.w);
-                q_ += fmaf(x.x, x.x, fmaf(x.y, x.y, fmaf(x.z, x.z, x.w * x.w)));
-                xw[(j & 1) * 2] = pack_bf16(x.x, x.y);
-                xw[(j & 1) * 2 + 1] = pack_bf16(x.z, x.w);
-                if (j & 1)   // 64-byte rows, 64 B swizzle: chunk ^= (row >> 1) & 3
-                  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(xrow + (((j >> 1) ^ ((lane >> 1) & 3)) << 4)),
-                               "r"(xw[0]), "r"(xw[1]), "r"(xw[2]), "r"(xw[3])
-                               : "memory");
+                s_ += (x[j].x + x[j].y) + (x[j].z + x[j].w);
+                q_ += fmaf(x[j].x, x[j].x, fmaf(x[j].y, x[j].y, fmaf(x[j].z, x[j].z, x[j].w * x[j].w)));
               }
+#pragma unroll
+              for (int k = 0; k < 4; ++k)   // 64-byte rows, 64 B swizzle: chunk ^= (row >> 1) & 3
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(xrow + ((k ^ ((lane >> 1) & 3)) << 4)),
+                             "r"(pack_bf16(x[2 * k].x, x[2 * k].y)), "r"(pack_bf16(x[2 * k].z, x[2 * k].w)),
+                             "r"(pack_bf16(x[2 * k + 1].x, x[2 * k + 1].y)), "r"(pack_bf16(x[2 * k + 1].z, x[2 * k + 1].w))
+                             : "memory");
             }
             fence_proxy_async();
             __syncwarp();
@@ -430,7 +448,7 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
             }
             if (ln_out && row0 + lane < p.M)
               p.ln_stat_out[(long long)(col >> 5) * p.ln_stat_ld + row0 + lane] = make_float2(s_, q_);
-            ++bc;
+            if (++slot == R) { slot = 0; ph ^= 1; }
           }
           if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
