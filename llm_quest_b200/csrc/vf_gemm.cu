@@ -56,6 +56,7 @@ struct GemmParams {
   const int* dst_rows;
   int vec_ok;          // out (and res) rows are 16-byte aligned: 128-bit stores allowed
   int res_tma;         // residual epilogue through TMA (identity row map, N % 32 == 0): see the RING path
+  int out_tma;         // bf16 epilogues (bias / GELU): math on accumulator rows, 32x32 bf16 blocks TMA-stored
   int n_peers;         // > 0: fused all-gather, every element goes to peer[0..n_peers) (NVLink peer memory) instead of out
   char* peer[8];
   // patch-embedding mode
@@ -88,7 +89,7 @@ struct SmemLayout {
   static constexpr int B_BYTES = (BN / CG) * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
-  static constexpr int EPI_OFF = BAR_OFF + (RING ? 1024 : 256);   // ring slots need 1024-byte alignment (128 B swizzle)
+  static constexpr int EPI_OFF = BAR_OFF + 1024;   // TMA-swizzled epilogue slots: swizzle phase = address bits, keep them tile-relative
   static constexpr int RING_WARP_BYTES = 3 * 4096;   // three fp32 slots, or two + the bf16 slot (folded-LN producer)
   static constexpr int EPI_BYTES = RING ? 8 * RING_WARP_BYTES : 4 * 8192;   // else: 32x32 fp32 staging blocks
   static constexpr int TOTAL = EPI_OFF + EPI_BYTES + 1024;  // + alignment slack
@@ -174,9 +175,9 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
     }
     if constexpr (RING) {
       tma_prefetch_desc(&em.res);
-      tma_prefetch_desc(&em.out);
       for (int i = 0; i < 24; ++i) mbar_init(&rfull_bar[i], 1);
     }
+    if (p.res_tma || p.out_tma) tma_prefetch_desc(&em.out);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -449,6 +450,95 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
             if (ln_out && row0 + lane < p.M)
               p.ln_stat_out[(long long)(col >> 5) * p.ln_stat_ld + row0 + lane] = make_float2(s_, q_);
             if (++slot == R) { slot = 0; ph ^= 1; }
+          }
+          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+        if (lane == 0) tma_store_wait<0>();
+      }
+    }
+
+    // ------------------------------------------------------------------ bf16 epilogues through a TMA store
+    // Same idea for bias / GELU (+ folded LayerNorm) outputs: the math runs on the accumulator ROW a thread gets from
+    // tcgen05.ld (bias and colsum are uniform broadcast loads, mean / rstd of the row are two scalars of the thread),
+    // the 32x32 bf16 block goes into a 64B-swizzled 2 KB slot with four 16-byte stores per thread and TMA writes it
+    // out: 64 KB of LSU traffic per 128x256 tile instead of 320 KB (stage fp32, read back, store), no transposition.
+    if constexpr (EPI == VF_EPI_BIAS_BF16 || EPI == VF_EPI_GELU_TANH_BF16 || EPI == VF_EPI_GELU_ERF_BF16) {
+      if (p.out_tma) {
+        ring_done = true;
+        const uint32_t slots = smem_u32(smem + L::EPI_OFF + (warp - 2) * 4096);   // two 2 KB slots per warp
+        const bool ln_fold = p.ln_row_stats != nullptr;
+        int sl = 0;
+        for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+          const int col0 = (tile % p.num_n_blk) * BN + chalf * COLS_PER_WARP;
+          const int row0 = ((tile / p.num_n_blk) * CG + rank) * BM + quarter * 32;
+          float mu = 0.f, rs = 1.f;
+          if (ln_fold) {
+            rs = 0.f;
+            if (row0 + lane < p.M) {
+              const float2 t = __ldg(p.ln_row_stats + row0 + lane);
+              mu = t.x; rs = t.y;
+            }
+          }
+          wait_or_trap(&tfull_bar[acc], acc_phase);
+          tc_fence_after();
+          const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + chalf * COLS_PER_WARP;
+#pragma unroll 1
+          for (int c = 0; c < COLS_PER_WARP / 32; ++c) {
+            const int col = col0 + c * 32;
+            const bool live = col < p.N;          // N % 32 == 0: a block is entirely inside or outside (uniform)
+            uint32_t r[32];
+            tmem_ld_x32(t_row + c * 32, r);
+            float4 bv[8], cs[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              bv[j] = (live && p.bias) ? __ldg(reinterpret_cast<const float4*>(p.bias + col + 4 * j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+              cs[j] = (live && ln_fold) ? __ldg(reinterpret_cast<const float4*>(p.ln_colsum + col + 4 * j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            if (lane == 0) tma_store_wait_read<1>();   // the store that used this slot two blocks ago has left shared memory
+            __syncwarp();
+            tmem_ld_wait();
+            if (c == COLS_PER_WARP / 32 - 1) {         // all tcgen05.ld of this warp for the tile are complete
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) {
+                if (CG == 2) mbar_arrive_leader(&tempty_bar[acc]);
+                else mbar_arrive(&tempty_bar[acc]);
+              }
+            }
+            if (live) {
+              const uint32_t srow = slots + sl * 2048 + lane * 64;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                uint32_t w[4];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                  const int j = 2 * k + h;
+                  float v[4] = {__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                                __uint_as_float(r[4 * j + 3])};
+                  const float bb[4] = {bv[j].x, bv[j].y, bv[j].z, bv[j].w};
+                  const float cc4[4] = {cs[j].x, cs[j].y, cs[j].z, cs[j].w};
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    // identical expressions to the staged epilogue: both paths must give the same bits
+                    v[e] = ln_fold ? fmaf(rs, fmaf(-mu, cc4[e], v[e]), bb[e]) : v[e] + bb[e];
+                    if constexpr (EPI == VF_EPI_GELU_TANH_BF16) v[e] = gelu_tanh_f(v[e]);
+                    if constexpr (EPI == VF_EPI_GELU_ERF_BF16) v[e] = gelu_erf_f(v[e]);
+                  }
+                  w[2 * h] = pack_bf16(v[0], v[1]);
+                  w[2 * h + 1] = pack_bf16(v[2], v[3]);
+                }
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + ((k ^ ((lane >> 1) & 3)) << 4)), "r"(w[0]),
+                             "r"(w[1]), "r"(w[2]), "r"(w[3])
+                             : "memory");
+              }
+              fence_proxy_async();
+              __syncwarp();
+              if (lane == 0) {
+                tma_store_2d(&em.out, reinterpret_cast<const void*>(smem + L::EPI_OFF + (warp - 2) * 4096 + sl * 2048), col, row0);
+                tma_store_commit();
+              }
+              sl ^= 1;
+            }
           }
           if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
@@ -806,11 +896,11 @@ template <int BN, int CG>
 static int dispatch_epi(int mode, const GemmParams& p, const CUtensorMap& a, const CUtensorMap& b,
                         cudaStream_t s, const EpiMaps* em = nullptr) {
   switch (mode) {
-    case VF_EPI_BIAS_BF16: return launch_gemm<VF_EPI_BIAS_BF16, BN, false, CG>(p, a, b, s);
+    case VF_EPI_BIAS_BF16: return launch_gemm<VF_EPI_BIAS_BF16, BN, false, CG>(p, a, b, s, em);
     case VF_EPI_BIAS_F32: return launch_gemm<VF_EPI_BIAS_F32, BN, false, CG>(p, a, b, s);
     case VF_EPI_BIAS_RES_F32: return launch_gemm<VF_EPI_BIAS_RES_F32, BN, false, CG>(p, a, b, s, em);
-    case VF_EPI_GELU_TANH_BF16: return launch_gemm<VF_EPI_GELU_TANH_BF16, BN, false, CG>(p, a, b, s);
-    case VF_EPI_GELU_ERF_BF16: return launch_gemm<VF_EPI_GELU_ERF_BF16, BN, false, CG>(p, a, b, s);
+    case VF_EPI_GELU_TANH_BF16: return launch_gemm<VF_EPI_GELU_TANH_BF16, BN, false, CG>(p, a, b, s, em);
+    case VF_EPI_GELU_ERF_BF16: return launch_gemm<VF_EPI_GELU_ERF_BF16, BN, false, CG>(p, a, b, s, em);
     case VF_EPI_QKV_ROPE_BF16: return launch_gemm<VF_EPI_QKV_ROPE_BF16, BN, false, CG>(p, a, b, s);
     case VF_EPI_SCATTER_BF16: return launch_gemm<VF_EPI_SCATTER_BF16, BN, false, CG>(p, a, b, s);
     default: break;
@@ -961,9 +1051,23 @@ extern "C" int vf_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t l
     }
     p.res_tma = 1;
   }
+  static int out_tma_env = -1;
+  if (out_tma_env < 0) {
+    const char* e_ = getenv("VF_OUT_TMA");
+    out_tma_env = e_ ? atoi(e_) : 1;
+  }
+  if ((ep->mode == VF_EPI_BIAS_BF16 || ep->mode == VF_EPI_GELU_TANH_BF16 || ep->mode == VF_EPI_GELU_ERF_BF16) &&
+      ep->grp_rows <= 0 && p.n_peers == 0 && vec_ok && (N % 32) == 0 && out_tma_env) {
+    uint64_t dims[2] = {(uint64_t)N, (uint64_t)M};
+    uint32_t box[2] = {32, 32};
+    uint64_t so[1] = {(uint64_t)ep->ldo * 2};
+    int e = encode_tmap(&em.out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, ep->out, dims, so, box, CU_TENSOR_MAP_SWIZZLE_64B);
+    if (e) return e;
+    p.out_tma = 1;
+  }
   if (cg == 2) return dispatch_epi<256, 2>(ep->mode, p, tmA, tmB, s, &em);
-  return bn == 256 ? dispatch_epi<256, 1>(ep->mode, p, tmA, tmB, s)
-                   : dispatch_epi<128, 1>(ep->mode, p, tmA, tmB, s);
+  return bn == 256 ? dispatch_epi<256, 1>(ep->mode, p, tmA, tmB, s, &em)
+                   : dispatch_epi<128, 1>(ep->mode, p, tmA, tmB, s, &em);
 }
 
 extern "C" int vf_patch_embed(const void* pixels, int32_t B, int32_t C, int32_t T, int32_t H,

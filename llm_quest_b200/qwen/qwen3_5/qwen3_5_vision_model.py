@@ -98,7 +98,7 @@ def ln_fusion_mode() -> int:
     only (lin2 / patch embedding produce, QKV consumes), 2 = norm1 and norm2 (proj produces, lin1 consumes)."""
     import os
 
-    return int(os.environ.get("VF_LN_FUSE", "1"))
+    return int(os.environ.get("VF_LN_FUSE", "2"))
 
 
 def _as_2d_bf16(x: torch.Tensor) -> torch.Tensor:
