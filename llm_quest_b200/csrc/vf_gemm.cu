@@ -99,8 +99,6 @@ struct EpiMaps {   // tensor maps of the TMA residual epilogue (32x32 boxes): re
   CUtensorMap res, out, xb;
 };
 
-template <int EPI, bool PATCH, int CG>
-constexpr bool kRing = (EPI == VF_EPI_BIAS_RES_F32 && !PATCH && CG == 2);
 
 __device__ __forceinline__ void wait_or_trap(uint64_t* bar, uint32_t parity) {
   // Bounded wait: a protocol bug becomes a trap (CUDA error) instead of a hung GPU.
@@ -138,12 +136,12 @@ __device__ __forceinline__ float gelu_erf_f(float x) {
   return x * (x < 0.f ? q : 1.0f - q);
 }
 
-template <int EPI, int BN, bool PATCH, int CG>
+template <int EPI, int BN, bool PATCH, int CG, bool RING = false>
 __global__ void __launch_bounds__(EpiCfg<EPI>::THREADS, 1)
 gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
             const __grid_constant__ CUtensorMap tmB, const __grid_constant__ EpiMaps em) {
   static_assert(CG == 1 || (CG == 2 && BN == 256 && !PATCH), "CTA pairs: 256-wide tiles, plain A operand");
-  constexpr bool RING = kRing<EPI, PATCH, CG>;
+  static_assert(!RING || (EPI == VF_EPI_BIAS_RES_F32 && !PATCH && CG == 2), "the TMA ring belongs to the CTA-pair residual kernel");
   using L = SmemLayout<BN, CG, RING>;
   constexpr int STAGES = L::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -869,14 +867,14 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-template <int EPI, int BN, bool PATCH = false, int CG = 1>
+template <int EPI, int BN, bool PATCH = false, int CG = 1, bool RING = false>
 static int launch_gemm(const GemmParams& p, const CUtensorMap& tmA, const CUtensorMap& tmB,
                        cudaStream_t stream, const EpiMaps* em_in = nullptr) {
-  using L = SmemLayout<BN, CG, kRing<EPI, PATCH, CG>>;
+  using L = SmemLayout<BN, CG, RING>;
   static const EpiMaps no_maps{};
   const EpiMaps& em = em_in ? *em_in : no_maps;
   static bool configured = false;
-  auto kfn = gemm_kernel<EPI, BN, PATCH, CG>;
+  auto kfn = gemm_kernel<EPI, BN, PATCH, CG, RING>;
   if (!configured) {
     VF_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     configured = true;
@@ -898,7 +896,11 @@ static int dispatch_epi(int mode, const GemmParams& p, const CUtensorMap& a, con
   switch (mode) {
     case VF_EPI_BIAS_BF16: return launch_gemm<VF_EPI_BIAS_BF16, BN, false, CG>(p, a, b, s, em);
     case VF_EPI_BIAS_F32: return launch_gemm<VF_EPI_BIAS_F32, BN, false, CG>(p, a, b, s);
-    case VF_EPI_BIAS_RES_F32: return launch_gemm<VF_EPI_BIAS_RES_F32, BN, false, CG>(p, a, b, s, em);
+    case VF_EPI_BIAS_RES_F32:
+      if constexpr (CG == 2) {
+        if (p.res_tma) return launch_gemm<VF_EPI_BIAS_RES_F32, BN, false, CG, true>(p, a, b, s, em);
+      }
+      return launch_gemm<VF_EPI_BIAS_RES_F32, BN, false, CG>(p, a, b, s, em);
     case VF_EPI_GELU_TANH_BF16: return launch_gemm<VF_EPI_GELU_TANH_BF16, BN, false, CG>(p, a, b, s, em);
     case VF_EPI_GELU_ERF_BF16: return launch_gemm<VF_EPI_GELU_ERF_BF16, BN, false, CG>(p, a, b, s, em);
     case VF_EPI_QKV_ROPE_BF16: return launch_gemm<VF_EPI_QKV_ROPE_BF16, BN, false, CG>(p, a, b, s);
@@ -1030,13 +1032,18 @@ extern "C" int vf_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t l
   }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   // TMA residual epilogue (VF_RES_TMA=0: the staged register epilogue, development A/B switch)
-  static int res_tma_env = -1;
+  // The ring takes two of the six main-loop stages: it pays where the epilogue bounds the kernel (short K: proj) and costs
+  // where the main loop does (K=3072, cold operands: lin2 211 vs 189 us under ncu), hence the K limit (VF_RES_TMA_MAXK).
+  static int res_tma_env = -1, res_tma_maxk = 1024;
   if (res_tma_env < 0) {
     const char* e_ = getenv("VF_RES_TMA");
     res_tma_env = e_ ? atoi(e_) : 1;
+    const char* k_ = getenv("VF_RES_TMA_MAXK");
+    if (k_) res_tma_maxk = atoi(k_);
   }
   EpiMaps em{};
   if (cg == 2 && ep->mode == VF_EPI_BIAS_RES_F32 && ep->grp_rows <= 0 && vec_ok && (N % 32) == 0 && res_tma_env &&
+      K <= res_tma_maxk &&
       (!p.ln_xb || ((p.ln_ldxb % 8) == 0 && (reinterpret_cast<uintptr_t>(p.ln_xb) & 15) == 0))) {
     uint64_t dims[2] = {(uint64_t)N, (uint64_t)M};
     uint32_t box[2] = {32, 32};

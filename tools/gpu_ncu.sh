@@ -24,8 +24,8 @@ ncu --set full --clock-control none --import-source on -k regex:gemm_kernel -s 7
 echo "gemm exit=$?"
 ncu --set full --clock-control none --import-source on -k regex:attention_kernel -s 17 -c 1 -o gpurun_out/prof_attn -f python /tmp/one_step.py 2 > gpurun_out/ncu_attn.log 2>&1
 echo "attn exit=$?"
-ncu --set full --clock-control none -k regex:layernorm_kernel -s 18 -c 1 -o gpurun_out/prof_ln -f python /tmp/one_step.py 2 > gpurun_out/ncu_ln.log 2>&1
+ncu --set full --clock-control none -k regex:layernorm_kernel -s 1 -c 1 -o gpurun_out/prof_ln -f python /tmp/one_step.py 2 > gpurun_out/ncu_ln.log 2>&1
 echo "ln exit=$?"
-ncu --set full --clock-control none -k regex:ln_row_stats_kernel -s 17 -c 1 -o gpurun_out/prof_rowstats -f python /tmp/one_step.py 2 > gpurun_out/ncu_rowstats.log 2>&1
+ncu --set full --clock-control none -k regex:ln_row_stats_kernel -s 30 -c 1 -o gpurun_out/prof_rowstats -f python /tmp/one_step.py 2 > gpurun_out/ncu_rowstats.log 2>&1
 echo "rowstats exit=$?"
 ls -la gpurun_out/*.ncu-rep
