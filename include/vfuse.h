@@ -103,6 +103,13 @@ typedef struct {
   int64_t ln_ldxb;
   void* ln_stat_out;         /* float2 [N/32][ln_stat_ld] or NULL (required with ln_xb_out) */
   int64_t ln_stat_ld;        /* rows per partial plane (>= M) */
+  /* optional (vf_gemm_bf16 producers): finish the statistics inside the same launch — the epilogue warp that
+   * completes a 32-row group (all N/32 partials stored) writes ln_rows_out[row] = (mean, rstd), eps = ln_eps, what
+   * vf_ln_row_stats() would compute. ln_counters: int32 [ceil(M/32)], zero before the first launch; the kernel leaves
+   * it zero again. */
+  void* ln_rows_out;         /* float2 [M] or NULL */
+  void* ln_counters;
+  float ln_eps;
   const void* ln_row_stats;  /* float2 [M] (mean, rstd) or NULL */
   const float* ln_colsum;    /* [N] fp32 (required with ln_row_stats) */
 } vf_epilogue;

@@ -59,6 +59,9 @@ class vf_epilogue(C.Structure):
         ("ln_ldxb", C.c_int64),
         ("ln_stat_out", C.c_void_p),
         ("ln_stat_ld", C.c_int64),
+        ("ln_rows_out", C.c_void_p),
+        ("ln_counters", C.c_void_p),
+        ("ln_eps", C.c_float),
         ("ln_row_stats", C.c_void_p),
         ("ln_colsum", C.c_void_p),
     ]
@@ -206,7 +209,8 @@ def gemm(a, w, mode, out, bias=None, res=None, rope=None, dst_rows=None, grp_row
     """out = epilogue(a @ w.T). a [M,K] bf16 (row stride free), w [N,K] bf16, see vf_epilogue_mode.
     peer_ptrs: device pointers (ints) of up to 8 destination buffers shaped like `out` (fused all-gather: the rows
     are stored to every one of them, `out` only provides dtype and row pitch).
-    ln_out = (xb bf16 [rows, N], stat fp32 [N/32, rows, 2]): LayerNorm producer side (bias_res_f32 only).
+    ln_out = (xb bf16 [rows, N], stat fp32 [N/32, rows, 2][, rows_out fp32 [M, 2], counters int32, eps]): LayerNorm
+    producer side (bias_res_f32 only); with the optional triple the launch also writes (mean, rstd) per row.
     ln_in = (row_stats fp32 [M, 2] (mean, rstd) from ln_row_stats(), colsum fp32 [N]): LayerNorm consumer side
     (GELU / QKV+RoPE epilogues); `w` and `bias` must be the folded ones (qwen3_5_vision_model._fold_ln)."""
     _require_cuda(a, w, out, bias, res, dst_rows)
@@ -238,11 +242,17 @@ def gemm(a, w, mode, out, bias=None, res=None, rope=None, dst_rows=None, grp_row
     if bias is not None:
         assert bias.dtype == torch.float32 and bias.is_contiguous() and bias.numel() == N
     if ln_out is not None:
-        xb, stat = ln_out
+        xb, stat = ln_out[:2]
         _require_cuda(xb, stat)
         assert xb.dtype == torch.bfloat16 and xb.stride(-1) == 1 and stat.dtype == torch.float32 and stat.is_contiguous()
         assert stat.dim() == 3 and stat.shape[0] == N // 32 and stat.shape[2] == 2
         ep.ln_xb_out, ep.ln_ldxb, ep.ln_stat_out, ep.ln_stat_ld = xb.data_ptr(), xb.stride(-2), stat.data_ptr(), stat.shape[1]
+        if len(ln_out) > 2:     # (.., rows fp32 [M, 2], counters int32 [ceil(M/32)], eps): finish mean / rstd in the launch
+            rows_out, counters, eps = ln_out[2:]
+            _require_cuda(rows_out, counters)
+            assert rows_out.dtype == torch.float32 and rows_out.is_contiguous() and rows_out.shape == (M, 2)
+            assert counters.dtype == torch.int32 and counters.is_contiguous() and counters.numel() >= (M + 31) // 32
+            ep.ln_rows_out, ep.ln_counters, ep.ln_eps = rows_out.data_ptr(), counters.data_ptr(), float(eps)
     if ln_in is not None:
         row_stats, colsum = ln_in
         _require_cuda(row_stats, colsum)

@@ -72,6 +72,10 @@ struct GemmParams {
   long long ln_ldxb;
   float2* ln_stat_out;       // producer: [N/32][ln_stat_ld] partial (sum, sum of squares)
   long long ln_stat_ld;
+  float2* ln_rows_out;       // producer: [M] (mean, rstd), written by the warp that completes a 32-row group
+  int* ln_counters;          // producer: [ceil(M/32)] contribution counters, zero before and after every launch
+  int ln_contribs;           // contributions per 32-row group = N / columns per epilogue warp
+  float ln_eps;
   const float2* ln_row_stats;  // consumer: [M] (mean, rstd)
   const float* ln_colsum;      // consumer: [N]
 };
@@ -318,6 +322,35 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
                    : "memory");
     };
 
+    // Folded LayerNorm, producer side: once a warp has stored its partial sums of a tile it counts itself in; the warp
+    // that completes a 32-row group (all N/32 partials present) turns them into (mean, rstd) right away — no separate
+    // kernel between the two GEMMs, no atomics on the data, fixed summation order (j = 0, 1, ...).
+    [[maybe_unused]] auto ln_finalize = [&](int row_first) {
+      if (p.ln_rows_out == nullptr || row_first >= p.M) return;
+      __threadfence();                       // this warp's partial sums are visible device-wide
+      __syncwarp();
+      int old = 0;
+      if (lane == 0) old = atomicAdd(p.ln_counters + (row_first >> 5), 1);
+      old = __shfl_sync(0xffffffffu, old, 0);
+      if (old != p.ln_contribs - 1) return;
+      __threadfence();                       // ... and everybody else's are visible to this warp
+      const int row = row_first + lane;
+      if (row < p.M) {
+        const float2* sp = p.ln_stat_out + row;
+        const int parts = p.N >> 5;
+        const float inv_d = 1.0f / static_cast<float>(p.N);
+        float s_ = 0.f, q_ = 0.f;
+#pragma unroll 8
+        for (int j = 0; j < parts; ++j) {
+          const float2 t = __ldcg(sp + (long long)j * p.ln_stat_ld);
+          s_ += t.x; q_ += t.y;
+        }
+        const float mu = s_ * inv_d;
+        p.ln_rows_out[row] = make_float2(mu, rsqrtf(fmaxf(fmaf(-mu, mu, q_ * inv_d), 0.f) + p.ln_eps));
+      }
+      if (lane == 0) p.ln_counters[row_first >> 5] = 0;   // ready for the next launch
+    };
+
     // Residual epilogue: the fp32 residual slab of a tile (128 KB) is pulled into L2 one tile ahead, while
     // the tensor pipe is still busy with the current one, so the epilogue's loads are L2 hits instead of
     // serialised DRAM round trips (measured: the proj GEMM, K=768, was bound by exactly that latency).
@@ -449,6 +482,7 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
               p.ln_stat_out[(long long)(col >> 5) * p.ln_stat_ld + row0 + lane] = make_float2(s_, q_);
             if (++slot == R) { slot = 0; ph ^= 1; }
           }
+          if (ln_out) ln_finalize(row0);
           if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
         if (lane == 0) tma_store_wait<0>();
@@ -843,6 +877,9 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
           }
         }
       }
+      if constexpr (EPI == VF_EPI_BIAS_RES_F32 && !PATCH) {
+        if (p.ln_xb != nullptr && p.grp_rows == 0) ln_finalize(m_blk * BM + quarter * 32);
+      }
       // release the accumulator buffer (all tcgen05.ld of this warp have completed)
       tc_fence_before();
       __syncwarp();
@@ -992,6 +1029,14 @@ extern "C" int vf_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t l
     p.ln_ldxb = ep->ln_ldxb;
     p.ln_stat_out = static_cast<float2*>(ep->ln_stat_out);
     p.ln_stat_ld = ep->ln_stat_ld;
+    if (ep->ln_rows_out) {
+      VF_REQUIRE(ep->ln_counters && (N % (bn / 2)) == 0 && (reinterpret_cast<uintptr_t>(ep->ln_rows_out) & 7) == 0, VF_ERR_ARG,
+                 "vf_gemm_bf16: ln_rows_out needs ln_counters and N %% %d == 0", bn / 2);
+      p.ln_rows_out = static_cast<float2*>(ep->ln_rows_out);
+      p.ln_counters = static_cast<int*>(ep->ln_counters);
+      p.ln_contribs = N / (bn / 2);
+      p.ln_eps = ep->ln_eps;
+    }
   }
   if (ep->ln_row_stats) {
     VF_REQUIRE(ep->mode == VF_EPI_GELU_TANH_BF16 || ep->mode == VF_EPI_GELU_ERF_BF16 || ep->mode == VF_EPI_QKV_ROPE_BF16,

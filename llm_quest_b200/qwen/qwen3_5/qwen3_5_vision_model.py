@@ -238,33 +238,34 @@ class Qwen3_5VisionTransformerBlock(nn.Module):
         self.ffn = Qwen3_5VisionFFN(cfg)
         self._packed = _Packed()
 
-    def run_(self, x2d, B, S, rope, work, ln1_ready=False, emit_next=False):
+    def run_(self, x2d, B, S, rope, work, ln1_ready=False, emit_next=False, rows_ready=False, next_eps=None):
         """In-place update of the fp32 residual stream x2d [B*S, D]; `work` holds reusable buffers.
 
-        With work["stat"] present both LayerNorms are folded into the GEMMs around them (vf_epilogue.ln_*): the GEMM
-        that produces x also writes its bf16 copy to work["h"] and per-row partial sums to work["stat"] (finalised into
-        work["rows"] = (mean, rstd) by a tiny kernel), the GEMM that consumes LN(x) multiplies the bf16 copy by the
-        gamma-scaled weight and normalises in its epilogue. ln1_ready:
-        the previous producer (patch embedding or the previous block's lin2) already left h/stat for norm1;
-        emit_next: this block's lin2 leaves them for the next block."""
+        With work["stat"] present the LayerNorms are folded into the GEMMs around them (vf_epilogue.ln_*): the GEMM that
+        produces x also writes its bf16 copy to work["h"], per-row partial sums to work["stat"] and — the warp that
+        completes a row group — (mean, rstd) to work["rows"]; the GEMM that consumes LN(x) multiplies the bf16 copy by
+        the gamma-scaled weight and normalises in its epilogue. ln1_ready: the previous producer (patch embedding or
+        the previous block's lin2) already left h/stat for norm1; rows_ready: it also left work["rows"] (the patch
+        embedding does not: vf_ln_row_stats finishes its partial sums); emit_next: this block's lin2 leaves them for the
+        next block, whose norm1 uses next_eps."""
         c = self._packed
         _, _, wo, bo = self.att.packed()
         w1, b1, w2, b2 = self.ffn.packed()
-        h, g, stat, rows = work["h"], work["g"], work.get("stat"), work.get("rows")
+        h, g, stat, rows, cnt = work["h"], work["g"], work.get("stat"), work.get("rows"), work.get("cnt")
         D = x2d.shape[1]
         if stat is not None and ln1_ready:
             wq, bq, csq = _fold_ln(c, "fold_qkv", self.att.qkv, self.norm1)
-            _lib.ln_row_stats(stat, D, self.norm1.eps, rows)
+            if not rows_ready:
+                _lib.ln_row_stats(stat, D, self.norm1.eps, rows)
             ctx = self.att.attend(h, B, S, rope, folded=(wq, bq), ln_in=(rows, csq))
         else:
             n1w, n1b = _f32(c, "n1w", self.norm1.weight), _f32(c, "n1b", self.norm1.bias)
             _lib.layernorm(x2d, n1w, n1b, h, self.norm1.eps)
             ctx = self.att.attend(h, B, S, rope)
-        nxt = (h, stat) if emit_next else None
+        nxt = (h, stat, rows, cnt, self.norm1.eps if next_eps is None else next_eps) if emit_next else None
         if stat is not None and work.get("fold_norm2"):
             w1f, b1f, cs1 = _fold_ln(c, "fold_lin1", self.ffn.lin1, self.norm2)
-            _lib.gemm(ctx, wo, VF_EPI_BIAS_RES_F32, x2d, bias=bo, res=x2d, ln_out=(h, stat))
-            _lib.ln_row_stats(stat, D, self.norm2.eps, rows)
+            _lib.gemm(ctx, wo, VF_EPI_BIAS_RES_F32, x2d, bias=bo, res=x2d, ln_out=(h, stat, rows, cnt, self.norm2.eps))
             _lib.gemm(h, w1f, VF_EPI_GELU_TANH_BF16, g, bias=b1f, ln_in=(rows, cs1))
             _lib.gemm(g, w2, VF_EPI_BIAS_RES_F32, x2d, bias=b2, res=x2d, ln_out=nxt)
             return
@@ -406,6 +407,9 @@ class Qwen3_5VisionModel(nn.Module):
             work["h"] = torch.empty((rows, D), dtype=torch.bfloat16, device=x.device)
             work["stat"] = torch.empty((D // 32, rows, 2), dtype=torch.float32, device=x.device)
             work["rows"] = torch.empty((rows, 2), dtype=torch.float32, device=x.device)
+            # contribution counters of the in-launch statistics (zero before and after every launch: allocated once)
+            work["cnt"] = self._packed.get(("ln_cnt", rows, str(x.device)), [],
+                                           lambda: torch.zeros(((rows + 31) // 32,), dtype=torch.int32, device=x.device))
             return work["h"], work["stat"]
 
         x2d, B, S = self.patch_embed.embed_into(x, pos, ln_work if fuse else None)
@@ -418,7 +422,8 @@ class Qwen3_5VisionModel(nn.Module):
             work["g"] = torch.empty((B * S, self.blocks[0].ffn.lin1.out_features), dtype=torch.bfloat16, device=x.device)
         last = len(self.blocks) - 1
         for i, block in enumerate(self.blocks):
-            block.run_(x2d, B, S, rope, work, ln1_ready=fuse, emit_next=fuse and i < last)
+            block.run_(x2d, B, S, rope, work, ln1_ready=fuse, emit_next=fuse and i < last, rows_ready=fuse and i > 0,
+                       next_eps=self.blocks[i + 1].norm1.eps if i < last else None)
         return x2d, B, S
 
     def forward(self, x, out=None, dst_rows=None, gather=None):

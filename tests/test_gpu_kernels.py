@@ -170,8 +170,13 @@ def test_gemm_residual_tma_epilogue_matches_staged_epilogue_bit_exact(L, with_ln
         n = x.shape[0]
         xb = torch.zeros((n, N), dtype=torch.bfloat16, device="cuda")
         stat = torch.full((N // 32, n, 2), float("nan"), device="cuda")
-        L.gemm(a[rows], w, L.VF_EPI_BIAS_RES_F32, x, bias=b, res=x, ln_out=(xb, stat) if with_ln else None)
-        return x.cpu(), xb.cpu(), stat.cpu()
+        mr = torch.full((n, 2), float("nan"), device="cuda")
+        cnt = torch.zeros(((n + 31) // 32,), dtype=torch.int32, device="cuda")
+        for _ in range(2):      # twice: the launch has to leave its contribution counters at zero
+            x.copy_(res[rows])
+            L.gemm(a[rows], w, L.VF_EPI_BIAS_RES_F32, x, bias=b, res=x, ln_out=(xb, stat, mr, cnt, 1e-6) if with_ln else None)
+        assert int(cnt.abs().sum()) == 0
+        return x.cpu(), xb.cpu(), stat.cpu(), mr.cpu()
 
     big = run(slice(0, M))
     check_close(big[0], ref, tol=2e-3, what="TMA residual epilogue vs fp32 oracle")
@@ -182,10 +187,13 @@ def test_gemm_residual_tma_epilogue_matches_staged_epilogue_bit_exact(L, with_ln
         if with_ln:
             assert torch.equal(big[1][lo:hi], small[1]), "bf16 copies differ"
             assert torch.equal(big[2][:, lo:hi], small[2]), "LayerNorm partial sums differ"
+            assert torch.equal(big[3][lo:hi], small[3]), "in-launch (mean, rstd) differ"
     if with_ln:
         assert torch.equal(big[1], bf(big[0]))
         blocks = big[0].view(M, N // 32, 32)
         torch.testing.assert_close(big[2][:, :, 0].t(), blocks.sum(-1), rtol=1e-5, atol=1e-4)
+        torch.testing.assert_close(big[3][:, 0], big[0].mean(1), rtol=1e-4, atol=1e-5)
+        torch.testing.assert_close(big[3][:, 1], (big[0].var(1, unbiased=False) + 1e-6).rsqrt(), rtol=1e-4, atol=1e-5)
 
 
 @pytest.mark.parametrize("mode", ["tanh", "erf", "qkv"])
