@@ -877,15 +877,15 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
           }
         }
       }
-      if constexpr (EPI == VF_EPI_BIAS_RES_F32 && !PATCH) {
-        if (p.ln_xb != nullptr && p.grp_rows == 0) ln_finalize(m_blk * BM + quarter * 32);
-      }
       // release the accumulator buffer (all tcgen05.ld of this warp have completed)
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
         if (CG == 2) mbar_arrive_leader(&tempty_bar[acc]);   // the leader's MMA warp reuses the buffer pair-wide
         else mbar_arrive(&tempty_bar[acc]);
+      }
+      if constexpr (EPI == VF_EPI_BIAS_RES_F32 && !PATCH) {   // after the release: the fence inside must not stall the MMA warp
+        if (p.ln_xb != nullptr && p.grp_rows == 0) ln_finalize(m_blk * BM + quarter * 32);
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }

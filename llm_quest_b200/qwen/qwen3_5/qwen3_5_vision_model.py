@@ -262,10 +262,16 @@ class Qwen3_5VisionTransformerBlock(nn.Module):
             n1w, n1b = _f32(c, "n1w", self.norm1.weight), _f32(c, "n1b", self.norm1.bias)
             _lib.layernorm(x2d, n1w, n1b, h, self.norm1.eps)
             ctx = self.att.attend(h, B, S, rope)
-        nxt = (h, stat, rows, cnt, self.norm1.eps if next_eps is None else next_eps) if emit_next else None
+        inl = cnt is not None
+        nxt = None
+        if emit_next:
+            nxt = (h, stat, rows, cnt, self.norm1.eps if next_eps is None else next_eps) if inl else (h, stat)
         if stat is not None and work.get("fold_norm2"):
             w1f, b1f, cs1 = _fold_ln(c, "fold_lin1", self.ffn.lin1, self.norm2)
-            _lib.gemm(ctx, wo, VF_EPI_BIAS_RES_F32, x2d, bias=bo, res=x2d, ln_out=(h, stat, rows, cnt, self.norm2.eps))
+            _lib.gemm(ctx, wo, VF_EPI_BIAS_RES_F32, x2d, bias=bo, res=x2d,
+                      ln_out=(h, stat, rows, cnt, self.norm2.eps) if inl else (h, stat))
+            if not inl:
+                _lib.ln_row_stats(stat, D, self.norm2.eps, rows)
             _lib.gemm(h, w1f, VF_EPI_GELU_TANH_BF16, g, bias=b1f, ln_in=(rows, cs1))
             _lib.gemm(g, w2, VF_EPI_BIAS_RES_F32, x2d, bias=b2, res=x2d, ln_out=nxt)
             return
@@ -421,8 +427,16 @@ class Qwen3_5VisionModel(nn.Module):
         if len(self.blocks):
             work["g"] = torch.empty((B * S, self.blocks[0].ffn.lin1.out_features), dtype=torch.bfloat16, device=x.device)
         last = len(self.blocks) - 1
+        import os
+
+        # VF_LN_INLAUNCH=1: the producing GEMM finishes (mean, rstd) itself (vf_epilogue.ln_rows_out) instead of a
+        # vf_ln_row_stats launch. Measured: 23 launches (0.26 ms) saved, but the fence + 24 dependent L2 loads of the
+        # finishing warp cost the epilogue-bound proj GEMM more (+0.44 ms over the 24 residual GEMMs): off by default.
+        if os.environ.get("VF_LN_INLAUNCH", "0") != "1":
+            work["cnt"] = None
         for i, block in enumerate(self.blocks):
-            block.run_(x2d, B, S, rope, work, ln1_ready=fuse, emit_next=fuse and i < last, rows_ready=fuse and i > 0,
+            block.run_(x2d, B, S, rope, work, ln1_ready=fuse, emit_next=fuse and i < last,
+                       rows_ready=fuse and i > 0 and work.get("cnt") is not None,
                        next_eps=self.blocks[i + 1].norm1.eps if i < last else None)
         return x2d, B, S
 
