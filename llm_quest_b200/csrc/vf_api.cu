@@ -31,10 +31,12 @@ void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 bool pdl_enabled() {
   static int on = -1;
   if (on < 0) {
-    // opt-in (VF_PDL=1): measured neutral for throughput at batch 64 (12.9-13.1 ms per step either way, inside the
-    // power-cap noise) and worth 2-7 % for CUDA-graph latency at batch 1-4 (1.069 -> 0.998 ms at batch 1)
+    // on by default (VF_PDL=0 disables): with the folded LayerNorms the step has 24 tiny statistics kernels between its
+    // GEMMs and overlapping every kernel's prologue (barrier init, TMEM allocation, tensor-map prefetch) with its
+    // predecessor's tail is worth 0.12 ms of the 12.9 ms step (12.99 / 12.96 -> 12.88 / 12.83 ms, same box); it was
+    // neutral before that, and 2-7 % for CUDA-graph latency at batch 1-4 (1.069 -> 0.998 ms at batch 1)
     const char* e = getenv("VF_PDL");
-    on = (e && e[0] == '1') ? 1 : 0;
+    on = (e && e[0] == '0') ? 0 : 1;
   }
   return on != 0;
 }
