@@ -110,6 +110,13 @@ typedef struct {
   void* ln_rows_out;         /* float2 [M] or NULL */
   void* ln_counters;
   float ln_eps;
+  /* optional: no launch between producer and consumer at all. The consumer gets the producer's partial sums
+   * (ln_part_in = the producer's ln_stat_out, K/32 planes of ln_stat_ld rows, eps = ln_eps) and ln_row_stats as a
+   * WRITABLE float2 [M] buffer: the epilogue warps of its first column tile of every row block add the partials up while
+   * the tensor pipe works and publish (mean, rstd) there, the other column tiles wait for the per-32-row flag.
+   * ln_flags: int32 [ceil(rows/32)], shared by producer (clears the flags of the rows it rewrites) and consumer. */
+  const void* ln_part_in;
+  void* ln_flags;
   const void* ln_row_stats;  /* float2 [M] (mean, rstd) or NULL */
   const float* ln_colsum;    /* [N] fp32 (required with ln_row_stats) */
 } vf_epilogue;
@@ -135,11 +142,12 @@ int vf_patch_embed(const void* pixels, int32_t B, int32_t C, int32_t T, int32_t 
                    int64_t out_row_off, void* stream);
 
 /* vf_patch_embed that also emits the producer side of the folded LayerNorm (see vf_epilogue.ln_xb_out): the bf16 copy
- * of every output row and its N/32 partial (sum, sum of squares) — what the first block's norm1 + QKV GEMM consume. */
+ * of every output row and its N/32 partial (sum, sum of squares) — what the first block's norm1 + QKV GEMM consume.
+ * ln_flags (may be NULL): see vf_epilogue.ln_flags, cleared for the rows written. */
 int vf_patch_embed_ln(const void* pixels, int32_t B, int32_t C, int32_t T, int32_t H, int32_t W, int32_t P, int32_t tp,
                       const void* weight, const float* bias, const float* pos, int64_t ld_pos, int32_t N, float* out,
                       int64_t ldo, int64_t out_rows_per_sample, int64_t out_row_off, void* ln_xb_out, int64_t ln_ldxb,
-                      void* ln_stat_out, int64_t ln_stat_ld, void* stream);
+                      void* ln_stat_out, int64_t ln_stat_ld, void* ln_flags, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Fused bidirectional attention, head_dim 64, bf16 in/out, fp32 softmax (tcgen05 + TMEM).

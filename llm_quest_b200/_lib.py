@@ -62,6 +62,8 @@ class vf_epilogue(C.Structure):
         ("ln_rows_out", C.c_void_p),
         ("ln_counters", C.c_void_p),
         ("ln_eps", C.c_float),
+        ("ln_part_in", C.c_void_p),
+        ("ln_flags", C.c_void_p),
         ("ln_row_stats", C.c_void_p),
         ("ln_colsum", C.c_void_p),
     ]
@@ -90,7 +92,7 @@ def lib() -> C.CDLL:
         "vf_gemm_bf16": [vp, i64, vp, i64, i32, i32, i32, C.POINTER(vf_epilogue), vp],
         "vf_patch_embed": [vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, i64, i32, vp, i64, i64, i64, vp],
         "vf_patch_embed_ln": [vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, i64, i32, vp, i64, i64, i64,
-                              vp, i64, vp, i64, vp],
+                              vp, i64, vp, i64, vp, vp],
         "vf_attention_fwd": [vp, vp, i32, i32, i32, f32, vp],
         "vf_attention_set_trace": [vp, i32, i32],
         "vf_attention_gqa_fwd": [vp, i64, i32, i32, vp, i64, vp, i64, vp, i64, vp, i64, i32, i32, i32, i32, i32, i32, i32,
@@ -212,7 +214,9 @@ def gemm(a, w, mode, out, bias=None, res=None, rope=None, dst_rows=None, grp_row
     ln_out = (xb bf16 [rows, N], stat fp32 [N/32, rows, 2][, rows_out fp32 [M, 2], counters int32, eps]): LayerNorm
     producer side (bias_res_f32 only); with the optional triple the launch also writes (mean, rstd) per row.
     ln_in = (row_stats fp32 [M, 2] (mean, rstd) from ln_row_stats(), colsum fp32 [N]): LayerNorm consumer side
-    (GELU / QKV+RoPE epilogues); `w` and `bias` must be the folded ones (qwen3_5_vision_model._fold_ln)."""
+    (GELU / QKV+RoPE epilogues); `w` and `bias` must be the folded ones (qwen3_5_vision_model._fold_ln). With three more
+    entries (partials, flags, eps) the launch finishes the statistics itself and row_stats is its scratch buffer; the
+    producer must then have been given the same flags tensor (ln_out = (xb, stat, flags))."""
     _require_cuda(a, w, out, bias, res, dst_rows)
     assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and a.dim() == 2 and w.dim() == 2
     assert a.stride(1) == 1 and w.stride(1) == 1 and out.stride(-1) == 1
@@ -247,18 +251,28 @@ def gemm(a, w, mode, out, bias=None, res=None, rope=None, dst_rows=None, grp_row
         assert xb.dtype == torch.bfloat16 and xb.stride(-1) == 1 and stat.dtype == torch.float32 and stat.is_contiguous()
         assert stat.dim() == 3 and stat.shape[0] == N // 32 and stat.shape[2] == 2
         ep.ln_xb_out, ep.ln_ldxb, ep.ln_stat_out, ep.ln_stat_ld = xb.data_ptr(), xb.stride(-2), stat.data_ptr(), stat.shape[1]
-        if len(ln_out) > 2:     # (.., rows fp32 [M, 2], counters int32 [ceil(M/32)], eps): finish mean / rstd in the launch
+        if len(ln_out) == 3:    # (.., flags int32 [ceil(rows/32)]): clear the "published" flags of the rewritten rows
+            _require_cuda(ln_out[2])
+            assert ln_out[2].dtype == torch.int32 and ln_out[2].is_contiguous()
+            ep.ln_flags = ln_out[2].data_ptr()
+        if len(ln_out) == 5:    # (.., rows fp32 [M, 2], counters int32 [ceil(M/32)], eps): finish mean / rstd in the launch
             rows_out, counters, eps = ln_out[2:]
             _require_cuda(rows_out, counters)
             assert rows_out.dtype == torch.float32 and rows_out.is_contiguous() and rows_out.shape == (M, 2)
             assert counters.dtype == torch.int32 and counters.is_contiguous() and counters.numel() >= (M + 31) // 32
             ep.ln_rows_out, ep.ln_counters, ep.ln_eps = rows_out.data_ptr(), counters.data_ptr(), float(eps)
     if ln_in is not None:
-        row_stats, colsum = ln_in
+        row_stats, colsum = ln_in[:2]
         _require_cuda(row_stats, colsum)
         assert row_stats.dtype == torch.float32 and row_stats.is_contiguous() and row_stats.shape == (M, 2)
         assert colsum.dtype == torch.float32 and colsum.is_contiguous() and colsum.numel() == N
         ep.ln_row_stats, ep.ln_colsum = row_stats.data_ptr(), colsum.data_ptr()
+        if len(ln_in) > 2:      # (.., partials fp32 [K/32, rows, 2], flags int32, eps): statistics finished inside this launch
+            part, flags, eps = ln_in[2:]
+            _require_cuda(part, flags)
+            assert part.dtype == torch.float32 and part.is_contiguous() and part.shape[0] == K // 32 and part.shape[2] == 2
+            assert flags.dtype == torch.int32 and flags.is_contiguous() and flags.numel() >= (M + 31) // 32
+            ep.ln_part_in, ep.ln_flags, ep.ln_eps, ep.ln_stat_ld = part.data_ptr(), flags.data_ptr(), float(eps), part.shape[1]
     with _timed("gemm_" + _EPI_NAMES.get(mode, str(mode)), flops=2.0 * M * N * K):
         check(lib().vf_gemm_bf16(a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), M, N, K, C.byref(ep),
                                  _stream()), "vf_gemm_bf16")
@@ -283,9 +297,13 @@ def patch_embed(pixels, weight2d, bias, pos, out, P, tp, out_rows_per_sample, ou
     assert pixels.dtype == torch.bfloat16 and pixels.is_contiguous() and pixels.dim() == 5
     B, Cc, T, H, W = pixels.shape
     N = weight2d.shape[0]
-    xb_p = xb_ld = st_p = st_ld = 0
+    xb_p = xb_ld = st_p = st_ld = fl_p = 0
     if ln_out is not None:
-        xb, stat = ln_out
+        xb, stat = ln_out[:2]
+        if len(ln_out) > 2:
+            _require_cuda(ln_out[2])
+            assert ln_out[2].dtype == torch.int32 and ln_out[2].is_contiguous()
+            fl_p = ln_out[2].data_ptr()
         _require_cuda(xb, stat)
         assert xb.dtype == torch.bfloat16 and xb.stride(-1) == 1 and stat.dtype == torch.float32 and stat.is_contiguous()
         assert stat.dim() == 3 and stat.shape[0] == N // 32 and stat.shape[2] == 2
@@ -294,7 +312,7 @@ def patch_embed(pixels, weight2d, bias, pos, out, P, tp, out_rows_per_sample, ou
         check(
             lib().vf_patch_embed_ln(pixels.data_ptr(), B, Cc, T, H, W, P, tp, weight2d.data_ptr(), _p(bias), _p(pos),
                                     pos.stride(0) if pos is not None else 0, N, out.data_ptr(), out.stride(-2),
-                                    out_rows_per_sample, out_row_off, xb_p, xb_ld, st_p, st_ld, _stream()),
+                                    out_rows_per_sample, out_row_off, xb_p, xb_ld, st_p, st_ld, fl_p, _stream()),
             "vf_patch_embed_ln",
         )
     return out

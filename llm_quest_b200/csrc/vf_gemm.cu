@@ -76,7 +76,10 @@ struct GemmParams {
   int* ln_counters;          // producer: [ceil(M/32)] contribution counters, zero before and after every launch
   int ln_contribs;           // contributions per 32-row group = N / columns per epilogue warp
   float ln_eps;
-  const float2* ln_row_stats;  // consumer: [M] (mean, rstd)
+  const float2* ln_row_stats;  // consumer: [M] (mean, rstd); with ln_part_in it is the buffer the publishing warps fill
+  const float2* ln_part_in;    // consumer: [K/32][ln_stat_ld] partial sums of the producer (NULL: ln_row_stats is final)
+  int* ln_flags;               // [ceil(M/32)] "row group published": cleared by the producer, set by the consumer's
+                               // first column tile, polled by its other column tiles
   const float* ln_colsum;      // consumer: [N]
 };
 
@@ -322,6 +325,65 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
                    : "memory");
     };
 
+    // Folded LayerNorm, consumer side: (mean, rstd) of row row_first + lane. Either they are final already (a
+    // vf_ln_row_stats launch in between), or — ln_part_in — the epilogue warp of the FIRST column tile of a row block adds
+    // up the producer's N/32 partial sums while the tensor pipe works on its tile and publishes the 32 values (fence,
+    // flag); the warps of the other column tiles of that row block poll the flag. The publishing tile has the lowest
+    // tile index of its row block and every CTA of the persistent grid is resident, so a waiter only ever waits for a
+    // tile that is running or done; the producer GEMM cleared the flags (works under CUDA-graph replay: no epochs).
+    [[maybe_unused]] auto ln_fetch = [&](int row_first, bool publisher, float& mu, float& rs) {
+      mu = 0.f; rs = 0.f;
+      const int row = row_first + lane;
+      if (p.ln_part_in == nullptr) {
+        if (row < p.M) {
+          const float2 t = __ldg(p.ln_row_stats + row);
+          mu = t.x; rs = t.y;
+        }
+        return;
+      }
+      if (row_first >= p.M) return;
+      int* flag = p.ln_flags + (row_first >> 5);
+      float2* rows = const_cast<float2*>(p.ln_row_stats);
+      if (publisher) {
+        if (row < p.M) {
+          const float2* sp = p.ln_part_in + row;
+          const int parts = p.K >> 5;
+          const float inv_d = 1.0f / static_cast<float>(p.K);
+          float s_ = 0.f, q_ = 0.f;
+#pragma unroll 8
+          for (int j = 0; j < parts; ++j) {
+            const float2 t = __ldcg(sp + (long long)j * p.ln_stat_ld);
+            s_ += t.x; q_ += t.y;
+          }
+          mu = s_ * inv_d;
+          rs = rsqrtf(fmaxf(fmaf(-mu, mu, q_ * inv_d), 0.f) + p.ln_eps);
+          rows[row] = make_float2(mu, rs);
+        }
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(flag), "r"(1) : "memory");
+      } else {
+        if (lane == 0) {
+          int v = 0;
+          const long long t0 = clock64();
+          while (true) {
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+            if (v == 1) break;
+            if (clock64() - t0 > 4000000000LL) {
+              printf("vf_gemm: LayerNorm row statistics never published (block %d, row %d)\n", blockIdx.x, row_first);
+              __trap();
+            }
+            __nanosleep(64);
+          }
+        }
+        __syncwarp();
+        if (row < p.M) {
+          const float2 t = __ldcg(rows + row);
+          mu = t.x; rs = t.y;
+        }
+      }
+    };
+
     // Folded LayerNorm, producer side: once a warp has stored its partial sums of a tile it counts itself in; the warp
     // that completes a 32-row group (all N/32 partials present) turns them into (mean, rstd) right away — no separate
     // kernel between the two GEMMs, no atomics on the data, fixed summation order (j = 0, 1, ...).
@@ -406,6 +468,8 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
           const int col0 = (tile % p.num_n_blk) * BN + chalf * COLS_PER_WARP;
           const int row0 = ((tile / p.num_n_blk) * CG + rank) * BM + quarter * 32;
           prefetch_res(tile + tile_step);
+          if (p.ln_flags && ln_out && (tile % p.num_n_blk) == 0 && chalf == 0 && lane == 0 && row0 < p.M)
+            p.ln_flags[row0 >> 5] = 0;             // this row group's statistics are being rewritten
           const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + chalf * COLS_PER_WARP;
 #pragma unroll 1
           for (int c = 0; c < COLS_PER_WARP / 32; ++c) {
@@ -504,13 +568,7 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
           const int col0 = (tile % p.num_n_blk) * BN + chalf * COLS_PER_WARP;
           const int row0 = ((tile / p.num_n_blk) * CG + rank) * BM + quarter * 32;
           float mu = 0.f, rs = 1.f;
-          if (ln_fold) {
-            rs = 0.f;
-            if (row0 + lane < p.M) {
-              const float2 t = __ldg(p.ln_row_stats + row0 + lane);
-              mu = t.x; rs = t.y;
-            }
-          }
+          if (ln_fold) ln_fetch(row0, (tile % p.num_n_blk) == 0 && chalf == 0, mu, rs);
           wait_or_trap(&tfull_bar[acc], acc_phase);
           tc_fence_after();
           const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + chalf * COLS_PER_WARP;
@@ -658,13 +716,7 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
       [[maybe_unused]] float ln_mu = 0.f, ln_rs = 0.f;
       [[maybe_unused]] const bool ln_in = p.ln_row_stats != nullptr;
       if constexpr (EPI == VF_EPI_GELU_TANH_BF16 || EPI == VF_EPI_GELU_ERF_BF16 || EPI == VF_EPI_QKV_ROPE_BF16) {
-        if (ln_in) {
-          const int m = m_blk * BM + quarter * 32 + lane;
-          if (m < p.M) {
-            const float2 t = __ldg(p.ln_row_stats + m);
-            ln_mu = t.x; ln_rs = t.y;
-          }
-        }
+        if (ln_in) ln_fetch(m_blk * BM + quarter * 32, n_blk == 0 && chalf == 0, ln_mu, ln_rs);
       }
 
       wait_or_trap(&tfull_bar[acc], acc_phase);
@@ -851,7 +903,10 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
                                : "memory");
                   s_ += a_; q_ += b_;
                 }
-                if (lane_orow >= 0) p.ln_stat_out[(long long)(cc >> 5) * p.ln_stat_ld + lane_orow] = make_float2(s_, q_);
+                if (lane_orow >= 0) {
+                  p.ln_stat_out[(long long)(cc >> 5) * p.ln_stat_ld + lane_orow] = make_float2(s_, q_);
+                  if (p.ln_flags && cc < 32) p.ln_flags[lane_orow >> 5] = 0;   // first column block: statistics are being rewritten
+                }
               }
             }
             if (c + 1 < COLS_PER_WARP / 32) load_res(c + 1);
@@ -1029,6 +1084,7 @@ extern "C" int vf_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t l
     p.ln_ldxb = ep->ln_ldxb;
     p.ln_stat_out = static_cast<float2*>(ep->ln_stat_out);
     p.ln_stat_ld = ep->ln_stat_ld;
+    p.ln_flags = static_cast<int*>(ep->ln_flags);
     if (ep->ln_rows_out) {
       VF_REQUIRE(ep->ln_counters && (N % (bn / 2)) == 0 && (reinterpret_cast<uintptr_t>(ep->ln_rows_out) & 7) == 0, VF_ERR_ARG,
                  "vf_gemm_bf16: ln_rows_out needs ln_counters and N %% %d == 0", bn / 2);
@@ -1047,6 +1103,14 @@ extern "C" int vf_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t l
                VF_ERR_ALIGN, "vf_gemm_bf16: folded LayerNorm (consumer) needs aligned rows and N %% 4 == 0");
     p.ln_row_stats = static_cast<const float2*>(ep->ln_row_stats);
     p.ln_colsum = ep->ln_colsum;
+    if (ep->ln_part_in) {
+      VF_REQUIRE(ep->ln_flags && (K % 32) == 0 && ep->ln_stat_ld >= M && (reinterpret_cast<uintptr_t>(ep->ln_part_in) & 7) == 0,
+                 VF_ERR_ARG, "vf_gemm_bf16: ln_part_in needs ln_flags, K %% 32 == 0 and ln_stat_ld >= M");
+      p.ln_part_in = static_cast<const float2*>(ep->ln_part_in);
+      p.ln_flags = static_cast<int*>(ep->ln_flags);
+      p.ln_stat_ld = ep->ln_stat_ld;
+      p.ln_eps = ep->ln_eps;
+    }
   }
 
   // CTA pairs for every 256-wide problem with at least one full pair of row blocks per SM pair
@@ -1128,7 +1192,7 @@ extern "C" int vf_patch_embed(const void* pixels, int32_t B, int32_t C, int32_t 
                               float* out, int64_t ldo, int64_t out_rows_per_sample,
                               int64_t out_row_off, void* stream) {
   return vf_patch_embed_ln(pixels, B, C, T, H, W, P, tp, weight, bias, pos, ld_pos, N, out, ldo, out_rows_per_sample,
-                           out_row_off, nullptr, 0, nullptr, 0, stream);
+                           out_row_off, nullptr, 0, nullptr, 0, nullptr, stream);
 }
 
 extern "C" int vf_patch_embed_ln(const void* pixels, int32_t B, int32_t C, int32_t T, int32_t H,
@@ -1136,7 +1200,7 @@ extern "C" int vf_patch_embed_ln(const void* pixels, int32_t B, int32_t C, int32
                                  const float* bias, const float* pos, int64_t ld_pos, int32_t N,
                                  float* out, int64_t ldo, int64_t out_rows_per_sample,
                                  int64_t out_row_off, void* ln_xb_out, int64_t ln_ldxb, void* ln_stat_out,
-                                 int64_t ln_stat_ld, void* stream) {
+                                 int64_t ln_stat_ld, void* ln_flags, void* stream) {
   VF_REQUIRE(pixels && weight && out, VF_ERR_ARG, "vf_patch_embed: null pointer");
   VF_REQUIRE(B > 0 && C > 0 && T > 0 && H > 0 && W > 0 && N > 0, VF_ERR_ARG, "vf_patch_embed: bad shape");
   VF_REQUIRE(P == 16, VF_ERR_ARG,
@@ -1184,6 +1248,7 @@ extern "C" int vf_patch_embed_ln(const void* pixels, int32_t B, int32_t C, int32
     p.ln_ldxb = ln_ldxb;
     p.ln_stat_out = static_cast<float2*>(ln_stat_out);
     p.ln_stat_ld = ln_stat_ld;
+    p.ln_flags = static_cast<int*>(ln_flags);
   }
 
   CUtensorMap tmA, tmB;

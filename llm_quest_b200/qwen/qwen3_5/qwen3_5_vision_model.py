@@ -251,28 +251,41 @@ class Qwen3_5VisionTransformerBlock(nn.Module):
         c = self._packed
         _, _, wo, bo = self.att.packed()
         w1, b1, w2, b2 = self.ffn.packed()
-        h, g, stat, rows, cnt = work["h"], work["g"], work.get("stat"), work.get("rows"), work.get("cnt")
+        h, g, stat, rows, cnt, flags = (work["h"], work["g"], work.get("stat"), work.get("rows"), work.get("cnt"),
+                                        work.get("flags"))
         D = x2d.shape[1]
+        inl = cnt is not None            # producer finishes (mean, rstd) itself (VF_LN_INLAUNCH=1)
+        pub = flags is not None          # consumer finishes them itself: publish / poll through `flags` (default)
         if stat is not None and ln1_ready:
             wq, bq, csq = _fold_ln(c, "fold_qkv", self.att.qkv, self.norm1)
-            if not rows_ready:
-                _lib.ln_row_stats(stat, D, self.norm1.eps, rows)
-            ctx = self.att.attend(h, B, S, rope, folded=(wq, bq), ln_in=(rows, csq))
+            if pub:
+                ln_in = (rows, csq, stat, flags, self.norm1.eps)
+            else:
+                if not rows_ready:
+                    _lib.ln_row_stats(stat, D, self.norm1.eps, rows)
+                ln_in = (rows, csq)
+            ctx = self.att.attend(h, B, S, rope, folded=(wq, bq), ln_in=ln_in)
         else:
             n1w, n1b = _f32(c, "n1w", self.norm1.weight), _f32(c, "n1b", self.norm1.bias)
             _lib.layernorm(x2d, n1w, n1b, h, self.norm1.eps)
             ctx = self.att.attend(h, B, S, rope)
-        inl = cnt is not None
-        nxt = None
-        if emit_next:
-            nxt = (h, stat, rows, cnt, self.norm1.eps if next_eps is None else next_eps) if inl else (h, stat)
+
+        def producer_args(eps):
+            if pub:
+                return (h, stat, flags)
+            return (h, stat, rows, cnt, eps) if inl else (h, stat)
+
+        nxt = producer_args(self.norm1.eps if next_eps is None else next_eps) if emit_next else None
         if stat is not None and work.get("fold_norm2"):
             w1f, b1f, cs1 = _fold_ln(c, "fold_lin1", self.ffn.lin1, self.norm2)
-            _lib.gemm(ctx, wo, VF_EPI_BIAS_RES_F32, x2d, bias=bo, res=x2d,
-                      ln_out=(h, stat, rows, cnt, self.norm2.eps) if inl else (h, stat))
-            if not inl:
-                _lib.ln_row_stats(stat, D, self.norm2.eps, rows)
-            _lib.gemm(h, w1f, VF_EPI_GELU_TANH_BF16, g, bias=b1f, ln_in=(rows, cs1))
+            _lib.gemm(ctx, wo, VF_EPI_BIAS_RES_F32, x2d, bias=bo, res=x2d, ln_out=producer_args(self.norm2.eps))
+            if pub:
+                ln_in = (rows, cs1, stat, flags, self.norm2.eps)
+            else:
+                if not inl:
+                    _lib.ln_row_stats(stat, D, self.norm2.eps, rows)
+                ln_in = (rows, cs1)
+            _lib.gemm(h, w1f, VF_EPI_GELU_TANH_BF16, g, bias=b1f, ln_in=ln_in)
             _lib.gemm(g, w2, VF_EPI_BIAS_RES_F32, x2d, bias=b2, res=x2d, ln_out=nxt)
             return
         n2w, n2b = _f32(c, "n2w", self.norm2.weight), _f32(c, "n2b", self.norm2.bias)
@@ -409,14 +422,27 @@ class Qwen3_5VisionModel(nn.Module):
         fuse = mode > 0 and len(self.blocks) > 0 and self.pos_embed.embedding_dim % 32 == 0
         work["fold_norm2"] = mode > 1
 
+        import os
+
+        # who turns the producer's partial sums into (mean, rstd), VF_LN_STATS = "kernel" (default: a vf_ln_row_stats
+        # launch, 10 us, hidden further by programmatic dependent launch), "producer" (the producing GEMM's last-arriving
+        # warp per row group: fence + 24 dependent loads cost the epilogue-bound proj GEMM +0.44 ms per step) or
+        # "consumer" (the consuming GEMM's first column tile publishes, the others poll a flag: two serialised L2 round
+        # trips at every tile start, +2.3 ms per step). Both alternatives are kept for the record and tested.
+        who = os.environ.get("VF_LN_STATS", "producer" if os.environ.get("VF_LN_INLAUNCH") == "1" else "kernel")
+
         def ln_work(rows, D):
             work["h"] = torch.empty((rows, D), dtype=torch.bfloat16, device=x.device)
             work["stat"] = torch.empty((D // 32, rows, 2), dtype=torch.float32, device=x.device)
             work["rows"] = torch.empty((rows, 2), dtype=torch.float32, device=x.device)
-            # contribution counters of the in-launch statistics (zero before and after every launch: allocated once)
-            work["cnt"] = self._packed.get(("ln_cnt", rows, str(x.device)), [],
-                                           lambda: torch.zeros(((rows + 31) // 32,), dtype=torch.int32, device=x.device))
-            return work["h"], work["stat"]
+            groups = (rows + 31) // 32
+            if who == "producer":   # contribution counters (zero before and after every launch: allocated once)
+                work["cnt"] = self._packed.get(("ln_cnt", rows, str(x.device)), [],
+                                               lambda: torch.zeros((groups,), dtype=torch.int32, device=x.device))
+            if who == "consumer":   # "row group published" flags (cleared by every producer for the rows it rewrites)
+                work["flags"] = self._packed.get(("ln_flags", rows, str(x.device)), [],
+                                                 lambda: torch.zeros((groups,), dtype=torch.int32, device=x.device))
+            return (work["h"], work["stat"], work["flags"]) if who == "consumer" else (work["h"], work["stat"])
 
         x2d, B, S = self.patch_embed.embed_into(x, pos, ln_work if fuse else None)
         cos_h, sin_h = self._rope_half(x.device)
@@ -427,13 +453,6 @@ class Qwen3_5VisionModel(nn.Module):
         if len(self.blocks):
             work["g"] = torch.empty((B * S, self.blocks[0].ffn.lin1.out_features), dtype=torch.bfloat16, device=x.device)
         last = len(self.blocks) - 1
-        import os
-
-        # VF_LN_INLAUNCH=1: the producing GEMM finishes (mean, rstd) itself (vf_epilogue.ln_rows_out) instead of a
-        # vf_ln_row_stats launch. Measured: 23 launches (0.26 ms) saved, but the fence + 24 dependent L2 loads of the
-        # finishing warp cost the epilogue-bound proj GEMM more (+0.44 ms over the 24 residual GEMMs): off by default.
-        if os.environ.get("VF_LN_INLAUNCH", "0") != "1":
-            work["cnt"] = None
         for i, block in enumerate(self.blocks):
             block.run_(x2d, B, S, rope, work, ln1_ready=fuse, emit_next=fuse and i < last,
                        rows_ready=fuse and i > 0 and work.get("cnt") is not None,

@@ -235,6 +235,56 @@ def test_gemm_folded_layernorm_consumer(L, mode):
     check_close(out, ref, tol=6e-3, what=f"folded layernorm -> {mode}")
 
 
+@pytest.mark.parametrize("mode,M", [("tanh", 4500), ("qkv", 4704), ("erf", 300)])
+def test_gemm_folded_layernorm_statistics_published_by_the_consumer(L, mode, M):
+    """No launch between producer and consumer: the consumer's first column tile of every row block adds up the
+    producer's partial sums and publishes (mean, rstd), its other column tiles poll the per-32-row flag the producer
+    cleared. Run twice on the same buffers (flags must be cleared again), large M (many CTAs waiting on a publisher)
+    and small M (single-CTA kernels, staged epilogues)."""
+    nh, nw = 7, 7 * 2
+    n = nh * nw
+    D = 768
+    N = 3 * D if mode == "qkv" else 3072
+    a, w0, b0 = dev(bf(rnd(M, 128, seed=70))), dev(bf(rnd(D, 128, seed=71, scale=0.1))), dev(rnd(D, seed=72))
+    res = rnd(M, D, seed=73) * 2.0 + 0.5
+    gamma, beta = 1.0 + 0.2 * rnd(D, seed=74), 0.1 * rnd(D, seed=75)
+    w, b = rnd(N, D, seed=76, scale=0.05), rnd(N, seed=77)
+    wf, bfold, cs = _fold(w, b, gamma, beta)
+    wf, bfold, cs = dev(wf), dev(bfold), dev(cs)
+    xb = torch.empty((M, D), dtype=torch.bfloat16, device="cuda")
+    stat = torch.empty((D // 32, M, 2), device="cuda")
+    flags = torch.ones(((M + 31) // 32,), dtype=torch.int32, device="cuda")     # stale "published" flags on purpose
+    rows = torch.full((M, 2), float("nan"), device="cuda")
+    out = torch.zeros((M, N), dtype=torch.bfloat16, device="cuda")
+    cos, sin = VO.axial_rope_tables(10_000, 64, nh, nw)
+    rope = (dev(cos[:, :32].contiguous()), dev(sin[:, :32].contiguous()), n, 2 * D)
+    for it in range(2):
+        x = dev((res + it).clone())
+        L.gemm(a, w0, L.VF_EPI_BIAS_RES_F32, x, bias=b0, res=x, ln_out=(xb, stat, flags))
+        assert int(flags.sum()) == 0, "the producer has to clear the flags of the rows it rewrites"
+        if mode == "qkv":
+            L.gemm(xb, wf, L.VF_EPI_QKV_ROPE_BF16, out, bias=bfold, ln_in=(rows, cs, stat, flags, 1e-6), rope=rope)
+        else:
+            epi = L.VF_EPI_GELU_TANH_BF16 if mode == "tanh" else L.VF_EPI_GELU_ERF_BF16
+            L.gemm(xb, wf, epi, out, bias=bfold, ln_in=(rows, cs, stat, flags, 1e-6))
+        torch.cuda.synchronize()
+        assert int(flags.sum()) == flags.numel(), "every row group has to be published exactly once"
+        xr = x.cpu()
+        torch.testing.assert_close(rows[:, 0].cpu(), xr.mean(1), rtol=1e-4, atol=1e-5)
+        torch.testing.assert_close(rows[:, 1].cpu(), (xr.var(1, unbiased=False) + 1e-6).rsqrt(), rtol=1e-4, atol=1e-5)
+        lin = torch.nn.functional.layer_norm(xr, (D,), gamma, beta, 1e-6) @ w.t() + b
+        if mode == "qkv":
+            B_ = M // n
+            H = D // 64
+            qkv = lin.view(B_, n, 3, H, 64)
+            q, k, v = (qkv[:, :, i].transpose(1, 2) for i in range(3))
+            q, k = VO.rotate_half_apply(q, cos, sin), VO.rotate_half_apply(k, cos, sin)
+            ref = torch.stack([t.transpose(1, 2) for t in (q, k, v)], dim=2).reshape(M, N)
+        else:
+            ref = (VO.gelu_tanh if mode == "tanh" else VO.gelu_erf)(lin)
+        check_close(out, ref, tol=6e-3, what=f"consumer-published statistics -> {mode} (run {it})")
+
+
 def test_gemm_folded_layernorm_rejects_bad_arguments(L):
     M, N, K = 256, 768, 768
     a, w = dev(bf(rnd(M, K, seed=80))), dev(bf(rnd(N, K, seed=81)))
