@@ -4,15 +4,22 @@
 //
 // Replaces every nn.Linear / nn.ConvNd(k=s) on the reference's vision path (see include/vfuse.h
 // for the call-site list). Design:
-//   * one CTA per SM, static round-robin over 128 x BN output tiles (n fastest so that concurrently
-//     running CTAs share the same A rows in L2);
-//   * warp 0 / lane 0: TMA producer, 4-stage ring of {A 128x64, W BNx64} bf16 tiles, 128B swizzle;
-//   * warp 1 / lane 0: tcgen05.mma issuer (cta_group::1, M=128, N=BN, K=16 per instruction),
-//     accumulators double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps the
-//     main loop of tile i+1;
-//   * warps 2..9: epilogue. tcgen05.ld 32x32b gives every thread one output row, so bias, GELU,
-//     residual add, axial RoPE (pairs i / i+32 of a head live in the same thread) and the row
-//     remaps are all register-local.
+//   * persistent: one CTA per SM — or one CTA PAIR (cta_group::2, a 256 x 256 tile, each CTA stages its own 128 A rows
+//     and half of the W tile) for every 256-wide problem — static round-robin over the output tiles, n fastest so that
+//     concurrently running CTAs share the same A rows in L2;
+//   * warp 0 / lane 0: TMA producer, ring of {A 128x64, W (BN/CG)x64} bf16 stages (six for pairs, four otherwise),
+//     128B swizzle;
+//   * warp 1 / lane 0: tcgen05.mma issuer (M = 128 * CG, N = BN, K = 16 per instruction), accumulators double-buffered
+//     in TMEM (2 x BN columns) so the epilogue of tile i overlaps the main loop of tile i+1;
+//   * warps 2..9: epilogue. tcgen05.ld 32x32b gives every thread one accumulator ROW. Three epilogue families:
+//       - staged (RoPE, scatter, row remap, patch mode, small problems): 32x32 fp32 blocks are transposed through a
+//         private XOR-swizzled smem block so that all global I/O is coalesced;
+//       - bf16 rows + TMA store (bias / GELU, + folded LayerNorm): the math runs on the row, the 32x32 bf16 block is
+//         written to a 64B-swizzled slot and stored by TMA — a fifth of the LSU traffic, no transposition;
+//       - fp32 residual through TMA (short-K residual GEMMs): the residual block is TMA-loaded into a 128B-swizzled
+//         slot, the accumulator row is added in place, the slot is TMA-stored (template flag RING, four stages);
+//     plus the folded LayerNorm (producer: bf16 copy + partial row sums; consumer: rstd * (acc - mean * colsum) + b')
+//     and the fused all-gather (peer / multicast stores);
 //   * patch-embedding mode gathers the A tile with ONE 5-D TMA box per stage straight from the
 //     [B,C,T,H,W] pixel tensor (im2col-free): tile rows are a 16 x 8 rectangle of patches. A patch
 //     row is only 32 B wide, and TMA pads narrower-than-span rows under the 128 B swizzle (measured:

@@ -185,3 +185,31 @@ def test_hf_vision_weight_remap_round_trip():
     bad["model.visual.merger.linear_fc2.weight"] = torch.zeros(2, 2)
     with pytest.raises(ValueError, match="shape"):
         WL.convert_vision_weights(bad, dst.state_dict())
+
+
+def test_fold_layernorm_host_side_identity():
+    """_fold_ln (host side of the folded LayerNorm): rstd * (x W'^T - mean * colsum) + b' == LN(x) W^T + b in fp32 up to
+    the bf16 rounding of W' — and colsum is the sum of the ROUNDED weight, the one the tensor cores multiply by."""
+    from llm_quest_b200.qwen.qwen3_5.qwen3_5_vision_model import _Packed, _fold_ln, ln_fusion_mode
+
+    torch.manual_seed(3)
+    d, n = 96, 40
+    lin, norm = torch.nn.Linear(d, n), torch.nn.LayerNorm(d, eps=1e-6)
+    with torch.no_grad():
+        norm.weight.add_(0.3 * torch.randn(d))
+        norm.bias.add_(0.2 * torch.randn(d))
+    cache = _Packed()
+    wf, bf_, cs = _fold_ln(cache, "k", lin, norm)
+    assert wf.dtype == torch.bfloat16 and bf_.dtype == torch.float32 and cs.dtype == torch.float32
+    assert torch.equal(cs, wf.float().sum(1))
+    assert _fold_ln(cache, "k", lin, norm)[0] is wf, "folded weights are cached until a parameter changes"
+    x = torch.randn(17, d) * 2 + 0.7
+    mean, rstd = x.mean(1, keepdim=True), (x.var(1, unbiased=False, keepdim=True) + 1e-6).rsqrt()
+    with torch.no_grad():
+        folded = rstd * (x @ wf.float().t() - mean * cs[None]) + bf_[None]
+        ref = lin(norm(x))
+    assert (folded - ref).abs().max() / ref.abs().max() < 5e-3      # bf16 rounding of gamma . W only
+    with torch.no_grad():
+        norm.weight.mul_(1.5)                                       # in-place edit bumps _version: cache must rebuild
+    assert _fold_ln(cache, "k", lin, norm)[0] is not wf
+    assert ln_fusion_mode() in (0, 1, 2)
