@@ -112,9 +112,10 @@ typedef struct {
   float ln_eps;
   /* optional: no launch between producer and consumer at all. The consumer gets the producer's partial sums
    * (ln_part_in = the producer's ln_stat_out, K/32 planes of ln_stat_ld rows, eps = ln_eps) and ln_row_stats as a
-   * WRITABLE float2 [M] buffer: the epilogue warps of its first column tile of every row block add the partials up while
-   * the tensor pipe works and publish (mean, rstd) there, the other column tiles wait for the per-32-row flag.
-   * ln_flags: int32 [ceil(rows/32)], shared by producer (clears the flags of the rows it rewrites) and consumer. */
+   * WRITABLE float2 [M] buffer: before their first tile the epilogue warps of the (persistent, fully resident) grid add
+   * the partials up, one 32-row group per warp and round, and count themselves in; the first epilogue of every warp
+   * waits for the full count. ln_flags: int32 [1], that counter — the PRODUCER launch clears it (give it the same
+   * pointer), so the pair also works under CUDA-graph replay. */
   const void* ln_part_in;
   void* ln_flags;
   const void* ln_row_stats;  /* float2 [M] (mean, rstd) or NULL */
@@ -143,7 +144,7 @@ int vf_patch_embed(const void* pixels, int32_t B, int32_t C, int32_t T, int32_t 
 
 /* vf_patch_embed that also emits the producer side of the folded LayerNorm (see vf_epilogue.ln_xb_out): the bf16 copy
  * of every output row and its N/32 partial (sum, sum of squares) — what the first block's norm1 + QKV GEMM consume.
- * ln_flags (may be NULL): see vf_epilogue.ln_flags, cleared for the rows written. */
+ * ln_flags (may be NULL): see vf_epilogue.ln_flags, cleared by this launch. */
 int vf_patch_embed_ln(const void* pixels, int32_t B, int32_t C, int32_t T, int32_t H, int32_t W, int32_t P, int32_t tp,
                       const void* weight, const float* bias, const float* pos, int64_t ld_pos, int32_t N, float* out,
                       int64_t ldo, int64_t out_rows_per_sample, int64_t out_row_off, void* ln_xb_out, int64_t ln_ldxb,

@@ -85,8 +85,8 @@ struct GemmParams {
   float ln_eps;
   const float2* ln_row_stats;  // consumer: [M] (mean, rstd); with ln_part_in it is the buffer the publishing warps fill
   const float2* ln_part_in;    // consumer: [K/32][ln_stat_ld] partial sums of the producer (NULL: ln_row_stats is final)
-  int* ln_flags;               // [ceil(M/32)] "row group published": cleared by the producer, set by the consumer's
-                               // first column tile, polled by its other column tiles
+  int* ln_flags;               // [1] number of consumer epilogue warps that finished their share of the statistics:
+                               // cleared by the producer launch, counted up and polled by the consumer launch
   const float* ln_colsum;      // consumer: [N]
 };
 
@@ -332,62 +332,60 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
                    : "memory");
     };
 
-    // Folded LayerNorm, consumer side: (mean, rstd) of row row_first + lane. Either they are final already (a
-    // vf_ln_row_stats launch in between), or — ln_part_in — the epilogue warp of the FIRST column tile of a row block adds
-    // up the producer's N/32 partial sums while the tensor pipe works on its tile and publishes the 32 values (fence,
-    // flag); the warps of the other column tiles of that row block poll the flag. The publishing tile has the lowest
-    // tile index of its row block and every CTA of the persistent grid is resident, so a waiter only ever waits for a
-    // tile that is running or done; the producer GEMM cleared the flags (works under CUDA-graph replay: no epochs).
-    [[maybe_unused]] auto ln_fetch = [&](int row_first, bool publisher, float& mu, float& rs) {
-      mu = 0.f; rs = 0.f;
-      const int row = row_first + lane;
-      if (p.ln_part_in == nullptr) {
-        if (row < p.M) {
-          const float2 t = __ldg(p.ln_row_stats + row);
-          mu = t.x; rs = t.y;
-        }
-        return;
-      }
-      if (row_first >= p.M) return;
-      int* flag = p.ln_flags + (row_first >> 5);
-      float2* rows = const_cast<float2*>(p.ln_row_stats);
-      if (publisher) {
-        if (row < p.M) {
-          const float2* sp = p.ln_part_in + row;
-          const int parts = p.K >> 5;
-          const float inv_d = 1.0f / static_cast<float>(p.K);
-          float s_ = 0.f, q_ = 0.f;
+    // Folded LayerNorm, consumer side. (mean, rstd) per row are either final already (a vf_ln_row_stats launch in
+    // between) or — ln_part_in — finished by THIS launch: before their first tile the epilogue warps of the whole grid
+    // add up the producer's K/32 partial sums, one 32-row group per warp and round (9.6 MB at cfg-2, hidden behind the
+    // first tile's main loop), and count themselves in; the first epilogue waits until every warp of the grid has.
+    // Deadlock-free: the grid is persistent (every CTA resident); the producer GEMM cleared the counter.
+    [[maybe_unused]] bool ln_ready = p.ln_part_in == nullptr;
+    if constexpr (EPI == VF_EPI_GELU_TANH_BF16 || EPI == VF_EPI_GELU_ERF_BF16 || EPI == VF_EPI_QKV_ROPE_BF16) {
+      if (p.ln_part_in != nullptr) {
+        float2* rows = const_cast<float2*>(p.ln_row_stats);
+        const int parts = p.K >> 5, groups = (p.M + 31) >> 5;
+        const float inv_d = 1.0f / static_cast<float>(p.K);
+        for (int g = blockIdx.x * EpiCfg<EPI>::WARPS + (warp - 2); g < groups; g += gridDim.x * EpiCfg<EPI>::WARPS) {
+          const int row = g * 32 + lane;
+          if (row < p.M) {
+            const float2* sp = p.ln_part_in + row;
+            float s_ = 0.f, q_ = 0.f;
 #pragma unroll 8
-          for (int j = 0; j < parts; ++j) {
-            const float2 t = __ldcg(sp + (long long)j * p.ln_stat_ld);
-            s_ += t.x; q_ += t.y;
+            for (int j = 0; j < parts; ++j) {
+              const float2 t = __ldcg(sp + (long long)j * p.ln_stat_ld);
+              s_ += t.x; q_ += t.y;
+            }
+            const float mu = s_ * inv_d;
+            rows[row] = make_float2(mu, rsqrtf(fmaxf(fmaf(-mu, mu, q_ * inv_d), 0.f) + p.ln_eps));
           }
-          mu = s_ * inv_d;
-          rs = rsqrtf(fmaxf(fmaf(-mu, mu, q_ * inv_d), 0.f) + p.ln_eps);
-          rows[row] = make_float2(mu, rs);
         }
         __threadfence();
         __syncwarp();
-        if (lane == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(flag), "r"(1) : "memory");
-      } else {
+        if (lane == 0) atomicAdd(p.ln_flags, 1);
+      }
+    }
+    [[maybe_unused]] auto ln_fetch = [&](int row_first, float& mu, float& rs) {
+      mu = 0.f; rs = 0.f;
+      if (!ln_ready) {
         if (lane == 0) {
+          const int want = gridDim.x * EpiCfg<EPI>::WARPS;
           int v = 0;
           const long long t0 = clock64();
           while (true) {
-            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
-            if (v == 1) break;
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p.ln_flags) : "memory");
+            if (v >= want) break;
             if (clock64() - t0 > 4000000000LL) {
-              printf("vf_gemm: LayerNorm row statistics never published (block %d, row %d)\n", blockIdx.x, row_first);
+              printf("vf_gemm: LayerNorm row statistics incomplete (block %d: %d of %d warps)\n", blockIdx.x, v, want);
               __trap();
             }
-            __nanosleep(64);
+            __nanosleep(100);
           }
         }
         __syncwarp();
-        if (row < p.M) {
-          const float2 t = __ldcg(rows + row);
-          mu = t.x; rs = t.y;
-        }
+        ln_ready = true;
+      }
+      const int row = row_first + lane;
+      if (row < p.M) {
+        const float2 t = __ldcg(p.ln_row_stats + row);   // written during this launch in the ln_part_in mode: no .nc path
+        mu = t.x; rs = t.y;
       }
     };
 
@@ -475,8 +473,8 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
           const int col0 = (tile % p.num_n_blk) * BN + chalf * COLS_PER_WARP;
           const int row0 = ((tile / p.num_n_blk) * CG + rank) * BM + quarter * 32;
           prefetch_res(tile + tile_step);
-          if (p.ln_flags && ln_out && (tile % p.num_n_blk) == 0 && chalf == 0 && lane == 0 && row0 < p.M)
-            p.ln_flags[row0 >> 5] = 0;             // this row group's statistics are being rewritten
+          if (p.ln_flags && ln_out && (tile % p.num_n_blk) == 0 && chalf == 0 && lane == 0)
+            p.ln_flags[0] = 0;                     // the consumer's "statistics done" counter starts from zero
           const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + chalf * COLS_PER_WARP;
 #pragma unroll 1
           for (int c = 0; c < COLS_PER_WARP / 32; ++c) {
@@ -575,7 +573,7 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
           const int col0 = (tile % p.num_n_blk) * BN + chalf * COLS_PER_WARP;
           const int row0 = ((tile / p.num_n_blk) * CG + rank) * BM + quarter * 32;
           float mu = 0.f, rs = 1.f;
-          if (ln_fold) ln_fetch(row0, (tile % p.num_n_blk) == 0 && chalf == 0, mu, rs);
+          if (ln_fold) ln_fetch(row0, mu, rs);
           wait_or_trap(&tfull_bar[acc], acc_phase);
           tc_fence_after();
           const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + chalf * COLS_PER_WARP;
@@ -723,7 +721,7 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
       [[maybe_unused]] float ln_mu = 0.f, ln_rs = 0.f;
       [[maybe_unused]] const bool ln_in = p.ln_row_stats != nullptr;
       if constexpr (EPI == VF_EPI_GELU_TANH_BF16 || EPI == VF_EPI_GELU_ERF_BF16 || EPI == VF_EPI_QKV_ROPE_BF16) {
-        if (ln_in) ln_fetch(m_blk * BM + quarter * 32, n_blk == 0 && chalf == 0, ln_mu, ln_rs);
+        if (ln_in) ln_fetch(m_blk * BM + quarter * 32, ln_mu, ln_rs);
       }
 
       wait_or_trap(&tfull_bar[acc], acc_phase);
@@ -912,7 +910,7 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
                 }
                 if (lane_orow >= 0) {
                   p.ln_stat_out[(long long)(cc >> 5) * p.ln_stat_ld + lane_orow] = make_float2(s_, q_);
-                  if (p.ln_flags && cc < 32) p.ln_flags[lane_orow >> 5] = 0;   // first column block: statistics are being rewritten
+                  if (p.ln_flags && cc < 32 && lane == 0) p.ln_flags[0] = 0;   // the consumer's "statistics done" counter
                 }
               }
             }

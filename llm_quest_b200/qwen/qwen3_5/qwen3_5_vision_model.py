@@ -424,11 +424,10 @@ class Qwen3_5VisionModel(nn.Module):
 
         import os
 
-        # who turns the producer's partial sums into (mean, rstd), VF_LN_STATS = "kernel" (default: a vf_ln_row_stats
-        # launch, 10 us, hidden further by programmatic dependent launch), "producer" (the producing GEMM's last-arriving
-        # warp per row group: fence + 24 dependent loads cost the epilogue-bound proj GEMM +0.44 ms per step) or
-        # "consumer" (the consuming GEMM's first column tile publishes, the others poll a flag: two serialised L2 round
-        # trips at every tile start, +2.3 ms per step). Both alternatives are kept for the record and tested.
+        # who turns the producer's partial sums into (mean, rstd), VF_LN_STATS = "kernel" (a vf_ln_row_stats launch),
+        # "consumer" (the consuming GEMM's epilogue warps do it grid-wide before their first tile, hidden behind the first
+        # main loop; a counter the producer cleared tells when all are done) or "producer" (the producing GEMM's
+        # last-arriving warp per row group: fence + 24 dependent loads cost the epilogue-bound proj GEMM +0.44 ms per step)
         who = os.environ.get("VF_LN_STATS", "producer" if os.environ.get("VF_LN_INLAUNCH") == "1" else "kernel")
 
         def ln_work(rows, D):
@@ -439,9 +438,9 @@ class Qwen3_5VisionModel(nn.Module):
             if who == "producer":   # contribution counters (zero before and after every launch: allocated once)
                 work["cnt"] = self._packed.get(("ln_cnt", rows, str(x.device)), [],
                                                lambda: torch.zeros((groups,), dtype=torch.int32, device=x.device))
-            if who == "consumer":   # "row group published" flags (cleared by every producer for the rows it rewrites)
-                work["flags"] = self._packed.get(("ln_flags", rows, str(x.device)), [],
-                                                 lambda: torch.zeros((groups,), dtype=torch.int32, device=x.device))
+            if who == "consumer":   # the consumer's "statistics done" counter (cleared by every producer launch)
+                work["flags"] = self._packed.get(("ln_flags", str(x.device)), [],
+                                                 lambda: torch.zeros((1,), dtype=torch.int32, device=x.device))
             return (work["h"], work["stat"], work["flags"]) if who == "consumer" else (work["h"], work["stat"])
 
         x2d, B, S = self.patch_embed.embed_into(x, pos, ln_work if fuse else None)
