@@ -497,7 +497,8 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
             float4 bv[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j)
-              bv[j] = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + col + 4 * j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+              bv[j] = (p.bias && col < p.N) ? __ldg(reinterpret_cast<const float4*>(p.bias + col + 4 * j))
+                                            : make_float4(0.f, 0.f, 0.f, 0.f);   // N % 32 == 0: a block is all in or all out
             wait_or_trap(&rf[slot], ph);
             const uint32_t rowb = ring_u + slot * 4096 + lane * 128;
             const uint32_t xrow = ring_u + 8192 + lane * 64;
@@ -547,7 +548,7 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
               if (ln_out) tma_store_2d(&em.xb, ring + 8192, col, row0);
               tma_store_commit();
             }
-            if (ln_out && row0 + lane < p.M)
+            if (ln_out && col < p.N && row0 + lane < p.M)   // (a block right of N is zero-filled by TMA and clipped on store)
               p.ln_stat_out[(long long)(col >> 5) * p.ln_stat_ld + row0 + lane] = make_float2(s_, q_);
             if (++slot == R) { slot = 0; ph ^= 1; }
           }

@@ -155,12 +155,13 @@ def test_gemm_folded_layernorm_producer(L, M):
     torch.testing.assert_close(stat[:, :, 1].cpu().t(), (blocks * blocks).sum(-1), rtol=1e-5, atol=1e-4)
 
 
+@pytest.mark.parametrize("N", [768, 800])
 @pytest.mark.parametrize("with_ln", [False, True])
-def test_gemm_residual_tma_epilogue_matches_staged_epilogue_bit_exact(L, with_ln):
+def test_gemm_residual_tma_epilogue_matches_staged_epilogue_bit_exact(L, with_ln, N):
     """Large M takes the CTA-pair kernel whose residual epilogue runs through TMA (32x32 blocks updated in place in
     shared memory); small M takes the single-CTA kernel with the staged register epilogue. Same rows, same bits —
     fp32 rows, bf16 copy and LayerNorm partial sums — and a ragged last row block (4500 = 35 * 128 + 20)."""
-    M, N, K = 4500, 768, 320
+    M, K = 4500, 320          # N = 800: the last 256-wide column tile is ragged (blocks right of N are skipped / clipped)
     a, w, b = dev(bf(rnd(M, K, seed=90))), dev(bf(rnd(N, K, seed=91, scale=0.05))), dev(rnd(N, seed=92))
     res = rnd(M, N, seed=93) + 0.25
     ref = a.float().cpu() @ w.float().cpu().t() + b.cpu() + res
@@ -172,11 +173,13 @@ def test_gemm_residual_tma_epilogue_matches_staged_epilogue_bit_exact(L, with_ln
         stat = torch.full((N // 32, n, 2), float("nan"), device="cuda")
         mr = torch.full((n, 2), float("nan"), device="cuda")
         cnt = torch.zeros(((n + 31) // 32,), dtype=torch.int32, device="cuda")
+        inl = N % 128 == 0      # in-launch (mean, rstd) need whole column ranges per epilogue warp
         for _ in range(2):      # twice: the launch has to leave its contribution counters at zero
             x.copy_(res[rows])
-            L.gemm(a[rows], w, L.VF_EPI_BIAS_RES_F32, x, bias=b, res=x, ln_out=(xb, stat, mr, cnt, 1e-6) if with_ln else None)
+            ln = ((xb, stat, mr, cnt, 1e-6) if inl else (xb, stat)) if with_ln else None
+            L.gemm(a[rows], w, L.VF_EPI_BIAS_RES_F32, x, bias=b, res=x, ln_out=ln)
         assert int(cnt.abs().sum()) == 0
-        return x.cpu(), xb.cpu(), stat.cpu(), mr.cpu()
+        return x.cpu(), xb.cpu(), stat.cpu(), mr.cpu() if inl else None
 
     big = run(slice(0, M))
     check_close(big[0], ref, tol=2e-3, what="TMA residual epilogue vs fp32 oracle")
@@ -187,13 +190,15 @@ def test_gemm_residual_tma_epilogue_matches_staged_epilogue_bit_exact(L, with_ln
         if with_ln:
             assert torch.equal(big[1][lo:hi], small[1]), "bf16 copies differ"
             assert torch.equal(big[2][:, lo:hi], small[2]), "LayerNorm partial sums differ"
-            assert torch.equal(big[3][lo:hi], small[3]), "in-launch (mean, rstd) differ"
+            if big[3] is not None:
+                assert torch.equal(big[3][lo:hi], small[3]), "in-launch (mean, rstd) differ"
     if with_ln:
         assert torch.equal(big[1], bf(big[0]))
         blocks = big[0].view(M, N // 32, 32)
         torch.testing.assert_close(big[2][:, :, 0].t(), blocks.sum(-1), rtol=1e-5, atol=1e-4)
-        torch.testing.assert_close(big[3][:, 0], big[0].mean(1), rtol=1e-4, atol=1e-5)
-        torch.testing.assert_close(big[3][:, 1], (big[0].var(1, unbiased=False) + 1e-6).rsqrt(), rtol=1e-4, atol=1e-5)
+        if big[3] is not None:
+            torch.testing.assert_close(big[3][:, 0], big[0].mean(1), rtol=1e-4, atol=1e-5)
+            torch.testing.assert_close(big[3][:, 1], (big[0].var(1, unbiased=False) + 1e-6).rsqrt(), rtol=1e-4, atol=1e-5)
 
 
 @pytest.mark.parametrize("mode", ["tanh", "erf", "qkv"])
