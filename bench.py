@@ -476,7 +476,7 @@ def run_ours(args):
     fused, overlap, gather_kind = None, None, "none"
     if world > 1 and wl.gather:
         try:
-            fused = parallel.FusedAllGather(rows_local=B * wl.n_out, cols=1024)
+            fused = parallel.FusedAllGather(rows_local=B * wl.n_out, cols=1024, slots=3)
             gather_kind = ("all-gather fused into the last GEMM (" + ("NVSwitch multimem stores" if fused.multicast_ptr else "NVLink peer stores")
                            + " + signal barrier)")
         except Exception as e:  # noqa: BLE001
@@ -485,6 +485,8 @@ def run_ours(args):
             gather_kind = "NCCL all-gather of merged embeddings on a side stream"
 
     def step_eager(inputs=dev_in):
+        if fused is not None:
+            fused.set_next_slot(0)       # slot 0: the resident step; slots 1, 2: the two ring slots of the e2e pipeline
         out = wl.ours_step(model, inputs, gather=fused)
         if overlap is not None:
             out, _ = overlap.submit(out.to(torch.bfloat16))
@@ -564,7 +566,8 @@ def run_ours(args):
                 return local_rows
             return out
 
-        enc = StreamedEncoder(e2e_model, depth=2, device=dev, graph=not args.no_graph and overlap is None)
+        enc = StreamedEncoder(e2e_model, depth=2, device=dev, graph=not args.no_graph and overlap is None,
+                              before_slot=(lambda i: fused.set_next_slot(1 + i)) if fused is not None else None)
         sink = [0.0]
 
         def run_e2e(steps):

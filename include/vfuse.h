@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define VF_VERSION 100 /* 0.1.0 */
+#define VF_VERSION 200 /* 0.2.0: one folded-LayerNorm protocol (row shift), multimem all-gather stores, head_dim != 64 attention */
 
 enum {
   VF_OK = 0,
@@ -90,35 +90,28 @@ typedef struct {
    * "GEMM, then ncclAllGather of its output" for the sample-sharded path. `out` is ignored. */
   int32_t n_peers;         /* 0 = store to `out` only */
   void* peer_out[8];
+  /* peer_out[0] is an NVSwitch MULTICAST mapping of the gathered buffer (n_peers must be 1): the epilogue writes it
+   * with multimem.st — the only instruction family that may touch such an address — and the switch replicates every
+   * store into all GPUs' copies. */
+  int32_t peer_multicast;
   /* LayerNorm folded into the two GEMMs around it (pre-LN block, qwen3_5_vision_model.py:195-238):
-   *   LN(x) @ W^T + b  =  rstd * (x @ (gamma.W)^T - mean * colsum) + (b + W beta),   colsum[n] = sum_k bf16(gamma_k W[n,k]).
-   * PRODUCER side (VF_EPI_BIAS_RES_F32, identity row map; also vf_patch_embed_ln): besides the fp32 row the epilogue
-   * writes its bf16 copy to ln_xb_out (the next GEMM's A operand) and, per 32-column block j, the partial row sums
-   * ln_stat_out[j * ln_stat_ld + row] = (sum x, sum x^2) as float2 — N/32 partials per row, no atomics, fixed order.
-   * vf_ln_row_stats() turns the partials into (mean, rstd) per row.
-   * CONSUMER side (VF_EPI_GELU_*_BF16, VF_EPI_QKV_ROPE_BF16): ln_row_stats holds (mean, rstd) of every row of A; the
-   * epilogue applies the identity above with ln_colsum [N] fp32. `bias` must already hold b + W beta and W must
-   * already be gamma-scaled (host side, once per weight). */
+   *   LN(x) @ W^T + b  =  rstd * (x' @ (gamma.W)^T - mean' * colsum) + (b + W beta),   colsum[n] = sum_k bf16(gamma_k W[n,k]),
+   * for ANY per-row shift s with x' = x - s and mean' = mean(x') (LayerNorm is shift-invariant). The bf16 rounding sits
+   * on x' instead of LN(x), so its error grows by sqrt(1 + (mean'/sigma)^2): with s = the row's mean at the previous
+   * LayerNorm point (the residual stream moves slowly) mean' stays far below sigma even for rows whose mean is 50 sigma.
+   * PRODUCER side (VF_EPI_BIAS_RES_F32, identity row map): besides the fp32 row x the epilogue writes bf16(x - ln_shift[row])
+   * to ln_xb_out (the next GEMM's A operand) and, per 32-column block j, the partial row sums
+   * ln_stat_out[j * ln_stat_ld + row] = (sum x', sum x'^2) as float2 — N/32 partials per row, no atomics, fixed order.
+   * vf_ln_row_stats() turns the partials into (mean', rstd) per row and advances the shift to the row's true mean.
+   * CONSUMER side (VF_EPI_GELU_*_BF16, VF_EPI_QKV_ROPE_BF16; N % 32 == 0): ln_row_stats holds (mean', rstd) of every row
+   * of A; the epilogue applies the identity above with ln_colsum [N] fp32. `bias` must already hold b + W beta and W
+   * must already be gamma-scaled (host side, once per weight). */
   void* ln_xb_out;           /* bf16 [rows, ln_ldxb] or NULL */
   int64_t ln_ldxb;
   void* ln_stat_out;         /* float2 [N/32][ln_stat_ld] or NULL (required with ln_xb_out) */
   int64_t ln_stat_ld;        /* rows per partial plane (>= M) */
-  /* optional (vf_gemm_bf16 producers): finish the statistics inside the same launch — the epilogue warp that
-   * completes a 32-row group (all N/32 partials stored) writes ln_rows_out[row] = (mean, rstd), eps = ln_eps, what
-   * vf_ln_row_stats() would compute. ln_counters: int32 [ceil(M/32)], zero before the first launch; the kernel leaves
-   * it zero again. */
-  void* ln_rows_out;         /* float2 [M] or NULL */
-  void* ln_counters;
-  float ln_eps;
-  /* optional: no launch between producer and consumer at all. The consumer gets the producer's partial sums
-   * (ln_part_in = the producer's ln_stat_out, K/32 planes of ln_stat_ld rows, eps = ln_eps) and ln_row_stats as a
-   * WRITABLE float2 [M] buffer: before their first tile the epilogue warps of the (persistent, fully resident) grid add
-   * the partials up, one 32-row group per warp and round, and count themselves in; the first epilogue of every warp
-   * waits for the full count. ln_flags: int32 [1], that counter — the PRODUCER launch clears it (give it the same
-   * pointer), so the pair also works under CUDA-graph replay. */
-  const void* ln_part_in;
-  void* ln_flags;
-  const void* ln_row_stats;  /* float2 [M] (mean, rstd) or NULL */
+  const float* ln_shift;     /* fp32 [M] row shifts or NULL (= 0) */
+  const void* ln_row_stats;  /* float2 [M] (mean', rstd) or NULL */
   const float* ln_colsum;    /* [N] fp32 (required with ln_row_stats) */
 } vf_epilogue;
 
@@ -142,14 +135,6 @@ int vf_patch_embed(const void* pixels, int32_t B, int32_t C, int32_t T, int32_t 
                    int64_t ld_pos, int32_t N, float* out, int64_t ldo, int64_t out_rows_per_sample,
                    int64_t out_row_off, void* stream);
 
-/* vf_patch_embed that also emits the producer side of the folded LayerNorm (see vf_epilogue.ln_xb_out): the bf16 copy
- * of every output row and its N/32 partial (sum, sum of squares) — what the first block's norm1 + QKV GEMM consume.
- * ln_flags (may be NULL): see vf_epilogue.ln_flags, cleared by this launch. */
-int vf_patch_embed_ln(const void* pixels, int32_t B, int32_t C, int32_t T, int32_t H, int32_t W, int32_t P, int32_t tp,
-                      const void* weight, const float* bias, const float* pos, int64_t ld_pos, int32_t N, float* out,
-                      int64_t ldo, int64_t out_rows_per_sample, int64_t out_row_off, void* ln_xb_out, int64_t ln_ldxb,
-                      void* ln_stat_out, int64_t ln_stat_ld, void* ln_flags, void* stream);
-
 /* ---------------------------------------------------------------------------------------------
  * Fused bidirectional attention, head_dim 64, bf16 in/out, fp32 softmax (tcgen05 + TMEM).
  * Replaces F.scaled_dot_product_attention(q,k,v) + the transposes around it
@@ -161,6 +146,11 @@ int vf_patch_embed_ln(const void* pixels, int32_t B, int32_t C, int32_t T, int32
  * ------------------------------------------------------------------------------------------- */
 int vf_attention_fwd(const void* qkv, void* out, int32_t B, int32_t S, int32_t H, float scale,
                      void* stream);
+/* Same contract for any head_dim that is a multiple of 8 up to 128 (qkv [B*S, 3*H*head_dim], out [B*S, H*head_dim]):
+ * head_dim 64 is the tensor-core kernel above; other head dims (TINY_VIT_CONFIG, config.py:175-186: head_dim 32, S = 65)
+ * run a CUDA-core kernel with K/V of a (sample, head) staged in shared memory (S <= 2048, 200 KB of shared memory). */
+int vf_attention_fwd_hd(const void* qkv, void* out, int32_t B, int32_t S, int32_t H, int32_t head_dim, float scale,
+                        void* stream);
 /* Diagnosis only: with a trace build selected (VF_ATTN_FLAGS bit 1) block 0 of every following
  * vf_attention_fwd writes clock64 stamps into buf — uint64 [20 chains][n_steps][8] — for the key steps
  * [first_step, first_step + n_steps) of each softmax chain / MMA walker. buf = NULL switches it off. */
@@ -192,13 +182,18 @@ int vf_attention_gqa_fwd(const void* q, int64_t ldq, int32_t q_col0, int32_t q_h
  * ------------------------------------------------------------------------------------------- */
 int vf_layernorm(const void* x, int32_t in_dtype, int64_t ldx, const float* w, const float* b,
                  void* out, int32_t out_dtype, int64_t rows, int32_t D, float eps, int32_t variant,
-                 int32_t merge, int32_t nh, int32_t nw, void* stream);
+                 int32_t merge, int32_t nh, int32_t nw, float* mean_out, void* stream);
+/* mean_out (fp32 [rows] or NULL): the row means, i.e. the first row shift of a chain of folded LayerNorms
+ * (vf_epilogue.ln_shift). */
 
-/* (mean, rstd) per row from the partial sums a folded-LayerNorm producer epilogue left (vf_epilogue.ln_stat_out):
- * partials float2 [parts][ld] -> out float2 [rows], mean = sum / D, rstd = rsqrt(max(sumsq / D - mean^2, 0) + eps).
- * Summation order is fixed (part 0, 1, ...), so results do not depend on the batch a row sits in. */
-int vf_ln_row_stats(const void* partials, int32_t parts, int64_t ld, int64_t rows, int32_t D, float eps, void* out,
-                    void* stream);
+/* (mean', rstd) per row from the partial sums a folded-LayerNorm producer epilogue left (vf_epilogue.ln_stat_out):
+ * partials float2 [parts][ld] -> out float2 [rows], mean' = sum / D, var = max(sumsq / D - mean'^2, 0),
+ * rstd = rsqrt(var + eps) (variant 0, nn.LayerNorm) or 1 / (sqrt(var) + eps) (variant 1, Part-1 LayerNorm).
+ * shift (fp32 [rows] or NULL): shift[row] += mean' — the producer subtracted shift[row], so this is the row's true mean,
+ * which the NEXT producer subtracts. Summation order is fixed (part 0, 1, ...): results do not depend on the batch a
+ * row sits in. */
+int vf_ln_row_stats(const void* partials, int32_t parts, int64_t ld, int64_t rows, int32_t D, float eps,
+                    int32_t variant, void* out, float* shift, void* stream);
 
 /* Part-1 class-token rows: out[b*S + 0, :] = cls[:] + pos[0, :]   (vit_model.py:86-87,145) */
 int vf_vit_cls_pos(const float* cls, const float* pos, float* out, int32_t B, int64_t rows_per_sample,
@@ -280,6 +275,35 @@ int vf_cast_bf16_to_f32(const void* x, float* out, int64_t n, void* stream);
  * ------------------------------------------------------------------------------------------- */
 int vf_preprocess_u8(const uint8_t* img, int32_t B, int32_t H, int32_t W, int32_t T, const float* mean3,
                      const float* std3, void* out, int32_t out_dtype, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Stand-alone pieces of the module surface (on the path proper they are GEMM epilogues or fused elsewhere).
+ * dtype: 0 = fp32, 1 = bf16 (in and out).
+ * ------------------------------------------------------------------------------------------- */
+/* GELU.forward of the Part-1 ViT (x * 0.5 * (1 + erf(x / sqrt 2)), vit_transformer_block.py:43-44; tanh_form = 0) and
+ * nn.GELU(approximate="tanh") (qwen3_5_vision_model.py:122; tanh_form = 1), erff / tanhf accuracy. */
+int vf_gelu(const void* x, void* out, int32_t dtype, int64_t n, int32_t tanh_form, void* stream);
+/* ZeroCenteredRMSNorm.forward (qwen/qwen3_next/qwen3_next_attention.py:41-46): fp32 inside,
+ * out = ((x * rsqrt(mean(x^2) + eps)) * one_plus_scale) cast back to dtype; one_plus_scale fp32 [D] = 1 + scale. */
+int vf_rmsnorm_zc(const void* x, int64_t ldx, const float* one_plus_scale, void* out, int64_t ldo, int32_t dtype,
+                  int64_t rows, int32_t D, float eps, void* stream);
+/* Part-2 text half of the early fusion: get_embeddings (multimodal/vlm_engine.py:5-20) + torch.cat([vision, text], 1)
+ * (vlm_engine.py:114, vlm_generation.py:66). out fp32 [b, rows_per_sample, D]:
+ *   out[bi, row_off + t, :] = tok_table[input_ids[bi, t], :] + pos_table[t, :]      (sum rounded to the tables' dtype)
+ * tables fp32 or bf16 (table_dtype), D % 8 == 0, seq <= n_pos. The vision rows [0, row_off) are written by the
+ * adapter's GEMM through its row remap (vf_epilogue.grp_rows). */
+int vf_embed_pos_concat(const int64_t* input_ids, const void* tok_table, int64_t vocab, const void* pos_table,
+                        int64_t n_pos, int32_t table_dtype, float* out, int32_t b, int32_t seq, int32_t D,
+                        int64_t rows_per_sample, int64_t row_off, void* stream);
+/* Patch sizes other than 16 (TINY_VIT_CONFIG: 4 x 4): pixels [B, C, H, W] (dtype) -> bf16 rows [B*nh*nw, ld_out],
+ * columns (c, py, px) = the flattened conv weight; the patch embedding is then vf_gemm_bf16 on those rows
+ * (vit_model.py:77-83). */
+int vf_im2col_patches(const void* pixels, int32_t dtype, int32_t B, int32_t C, int32_t H, int32_t W, int32_t P, void* out,
+                      int64_t ld_out, void* stream);
+/* out[b, r, :] = src[r, :] (+ add_row0[:] when r == 0) for every sample: the position-embedding (+ class token) rows
+ * the small-patch path accumulates its patch GEMM onto (vit_model.py:86-87,145). */
+int vf_fill_rows_f32(const float* src, const float* add_row0, float* out, int32_t B, int64_t rows_per_sample, int32_t D,
+                     void* stream);
 
 #ifdef __cplusplus
 }

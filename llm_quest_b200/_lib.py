@@ -27,9 +27,10 @@ VF_EPI_SCATTER_BF16 = 6
 
 EXPORTS = [
     "vf_version", "vf_last_error", "vf_launch_count", "vf_launch_count_reset", "vf_gemm_bf16",
-    "vf_patch_embed", "vf_patch_embed_ln", "vf_attention_fwd", "vf_attention_set_trace", "vf_attention_gqa_fwd", "vf_layernorm", "vf_ln_row_stats", "vf_vit_cls_pos", "vf_rope_apply",
+    "vf_patch_embed", "vf_attention_fwd", "vf_attention_fwd_hd", "vf_attention_set_trace", "vf_attention_gqa_fwd", "vf_layernorm", "vf_ln_row_stats", "vf_vit_cls_pos", "vf_rope_apply",
     "vf_mrope_apply", "vf_mrope_apply_strided", "vf_mrope_position_ids", "vf_fuse_scan", "vf_embed_gather_scatter",
     "vf_cast_f32_to_bf16", "vf_cast_bf16_to_f32", "vf_preprocess_u8",
+    "vf_gelu", "vf_rmsnorm_zc", "vf_embed_pos_concat", "vf_im2col_patches", "vf_fill_rows_f32",
 ]
 
 
@@ -55,15 +56,12 @@ class vf_epilogue(C.Structure):
         ("dst_rows", C.c_void_p),
         ("n_peers", C.c_int32),
         ("peer_out", C.c_void_p * 8),
+        ("peer_multicast", C.c_int32),
         ("ln_xb_out", C.c_void_p),
         ("ln_ldxb", C.c_int64),
         ("ln_stat_out", C.c_void_p),
         ("ln_stat_ld", C.c_int64),
-        ("ln_rows_out", C.c_void_p),
-        ("ln_counters", C.c_void_p),
-        ("ln_eps", C.c_float),
-        ("ln_part_in", C.c_void_p),
-        ("ln_flags", C.c_void_p),
+        ("ln_shift", C.c_void_p),
         ("ln_row_stats", C.c_void_p),
         ("ln_colsum", C.c_void_p),
     ]
@@ -91,14 +89,13 @@ def lib() -> C.CDLL:
     sigs = {
         "vf_gemm_bf16": [vp, i64, vp, i64, i32, i32, i32, C.POINTER(vf_epilogue), vp],
         "vf_patch_embed": [vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, i64, i32, vp, i64, i64, i64, vp],
-        "vf_patch_embed_ln": [vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, i64, i32, vp, i64, i64, i64,
-                              vp, i64, vp, i64, vp, vp],
         "vf_attention_fwd": [vp, vp, i32, i32, i32, f32, vp],
+        "vf_attention_fwd_hd": [vp, vp, i32, i32, i32, i32, f32, vp],
         "vf_attention_set_trace": [vp, i32, i32],
         "vf_attention_gqa_fwd": [vp, i64, i32, i32, vp, i64, vp, i64, vp, i64, vp, i64, i32, i32, i32, i32, i32, i32, i32,
                                  f32, i32, vp],
-        "vf_layernorm": [vp, i32, i64, vp, vp, vp, i32, i64, i32, f32, i32, i32, i32, i32, vp],
-        "vf_ln_row_stats": [vp, i32, i64, i64, i32, f32, vp, vp],
+        "vf_layernorm": [vp, i32, i64, vp, vp, vp, i32, i64, i32, f32, i32, i32, i32, i32, vp, vp],
+        "vf_ln_row_stats": [vp, i32, i64, i64, i32, f32, i32, vp, vp, vp],
         "vf_vit_cls_pos": [vp, vp, vp, i32, i64, i32, vp],
         "vf_rope_apply": [vp, vp, i32, i32, i32, i32, i32, vp, vp, i32, i64, vp, vp],
         "vf_mrope_apply": [vp, vp, i32, i32, i32, i32, i32, vp, vp, i32, i64, vp, i32, i32, i32, vp, f32, vp],
@@ -110,6 +107,11 @@ def lib() -> C.CDLL:
         "vf_cast_f32_to_bf16": [vp, vp, i64, vp],
         "vf_cast_bf16_to_f32": [vp, vp, i64, vp],
         "vf_preprocess_u8": [vp, i32, i32, i32, i32, C.POINTER(C.c_float), C.POINTER(C.c_float), vp, i32, vp],
+        "vf_gelu": [vp, vp, i32, i64, i32, vp],
+        "vf_rmsnorm_zc": [vp, i64, vp, vp, i64, i32, i64, i32, f32, vp],
+        "vf_embed_pos_concat": [vp, vp, i64, vp, i64, i32, vp, i32, i32, i32, i64, i64, vp],
+        "vf_im2col_patches": [vp, i32, i32, i32, i32, i32, i32, vp, i64, vp],
+        "vf_fill_rows_f32": [vp, vp, vp, i32, i64, i32, vp],
     }
     for name, args in sigs.items():
         fn = getattr(L, name)
@@ -207,16 +209,15 @@ _EPI_NAMES = {0: "bias_bf16", 1: "bias_f32", 2: "bias_res_f32", 3: "gelu_tanh_bf
 # tensor-level wrappers
 # ------------------------------------------------------------------------------------------------
 def gemm(a, w, mode, out, bias=None, res=None, rope=None, dst_rows=None, grp_rows=0, grp_stride=0, row_off=0,
-         peer_ptrs=None, ln_out=None, ln_in=None):
+         peer_ptrs=None, peer_multicast=False, ln_out=None, ln_in=None):
     """out = epilogue(a @ w.T). a [M,K] bf16 (row stride free), w [N,K] bf16, see vf_epilogue_mode.
     peer_ptrs: device pointers (ints) of up to 8 destination buffers shaped like `out` (fused all-gather: the rows
-    are stored to every one of them, `out` only provides dtype and row pitch).
-    ln_out = (xb bf16 [rows, N], stat fp32 [N/32, rows, 2][, rows_out fp32 [M, 2], counters int32, eps]): LayerNorm
-    producer side (bias_res_f32 only); with the optional triple the launch also writes (mean, rstd) per row.
-    ln_in = (row_stats fp32 [M, 2] (mean, rstd) from ln_row_stats(), colsum fp32 [N]): LayerNorm consumer side
-    (GELU / QKV+RoPE epilogues); `w` and `bias` must be the folded ones (qwen3_5_vision_model._fold_ln). With three more
-    entries (partials, flags, eps) the launch finishes the statistics itself and row_stats is its scratch buffer; the
-    producer must then have been given the same flags tensor (ln_out = (xb, stat, flags))."""
+    are stored to every one of them, `out` only provides dtype and row pitch); peer_multicast: the single pointer is an
+    NVSwitch multicast mapping (written with multimem.st).
+    ln_out = (xb bf16 [rows, N], stat fp32 [N/32, rows, 2][, shift fp32 [rows]]): LayerNorm producer side (bias_res_f32
+    only): bf16 copy and partial sums of the rows minus their shift.
+    ln_in = (row_stats fp32 [M, 2] (mean', rstd) from ln_row_stats(), colsum fp32 [N]): LayerNorm consumer side
+    (GELU / QKV+RoPE epilogues); `w` and `bias` must be the folded ones (qwen3_5_vision_model._fold_ln)."""
     _require_cuda(a, w, out, bias, res, dst_rows)
     assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and a.dim() == 2 and w.dim() == 2
     assert a.stride(1) == 1 and w.stride(1) == 1 and out.stride(-1) == 1
@@ -241,6 +242,7 @@ def gemm(a, w, mode, out, bias=None, res=None, rope=None, dst_rows=None, grp_row
     if peer_ptrs:
         assert len(peer_ptrs) <= 8
         ep.n_peers = len(peer_ptrs)
+        ep.peer_multicast = int(bool(peer_multicast))
         for i, ptr in enumerate(peer_ptrs):
             ep.peer_out[i] = int(ptr)
     if bias is not None:
@@ -251,80 +253,60 @@ def gemm(a, w, mode, out, bias=None, res=None, rope=None, dst_rows=None, grp_row
         assert xb.dtype == torch.bfloat16 and xb.stride(-1) == 1 and stat.dtype == torch.float32 and stat.is_contiguous()
         assert stat.dim() == 3 and stat.shape[0] == N // 32 and stat.shape[2] == 2
         ep.ln_xb_out, ep.ln_ldxb, ep.ln_stat_out, ep.ln_stat_ld = xb.data_ptr(), xb.stride(-2), stat.data_ptr(), stat.shape[1]
-        if len(ln_out) == 3:    # (.., flags int32 [1]): clear the consumer's "statistics done" counter
-            _require_cuda(ln_out[2])
-            assert ln_out[2].dtype == torch.int32 and ln_out[2].is_contiguous()
-            ep.ln_flags = ln_out[2].data_ptr()
-        if len(ln_out) == 5:    # (.., rows fp32 [M, 2], counters int32 [ceil(M/32)], eps): finish mean / rstd in the launch
-            rows_out, counters, eps = ln_out[2:]
-            _require_cuda(rows_out, counters)
-            assert rows_out.dtype == torch.float32 and rows_out.is_contiguous() and rows_out.shape == (M, 2)
-            assert counters.dtype == torch.int32 and counters.is_contiguous() and counters.numel() >= (M + 31) // 32
-            ep.ln_rows_out, ep.ln_counters, ep.ln_eps = rows_out.data_ptr(), counters.data_ptr(), float(eps)
+        if len(ln_out) > 2 and ln_out[2] is not None:
+            shift = ln_out[2]
+            _require_cuda(shift)
+            assert shift.dtype == torch.float32 and shift.is_contiguous() and shift.numel() >= M
+            ep.ln_shift = shift.data_ptr()
     if ln_in is not None:
-        row_stats, colsum = ln_in[:2]
+        row_stats, colsum = ln_in
         _require_cuda(row_stats, colsum)
         assert row_stats.dtype == torch.float32 and row_stats.is_contiguous() and row_stats.shape == (M, 2)
         assert colsum.dtype == torch.float32 and colsum.is_contiguous() and colsum.numel() == N
         ep.ln_row_stats, ep.ln_colsum = row_stats.data_ptr(), colsum.data_ptr()
-        if len(ln_in) > 2:      # (.., partials fp32 [K/32, rows, 2], flags int32, eps): statistics finished inside this launch
-            part, flags, eps = ln_in[2:]
-            _require_cuda(part, flags)
-            assert part.dtype == torch.float32 and part.is_contiguous() and part.shape[0] == K // 32 and part.shape[2] == 2
-            assert flags.dtype == torch.int32 and flags.is_contiguous() and flags.numel() >= 1
-            ep.ln_part_in, ep.ln_flags, ep.ln_eps, ep.ln_stat_ld = part.data_ptr(), flags.data_ptr(), float(eps), part.shape[1]
     with _timed("gemm_" + _EPI_NAMES.get(mode, str(mode)), flops=2.0 * M * N * K):
         check(lib().vf_gemm_bf16(a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), M, N, K, C.byref(ep),
                                  _stream()), "vf_gemm_bf16")
     return out
 
 
-def ln_row_stats(stat, D, eps, out):
-    """partials fp32 [parts, rows, 2] (a producer's ln_out stat) -> out fp32 [rows, 2] = (mean, rstd)."""
-    _require_cuda(stat, out)
+def ln_row_stats(stat, D, eps, out, shift=None, variant=0):
+    """partials fp32 [parts, rows, 2] (a producer's ln_out stat) -> out fp32 [rows, 2] = (mean of the shifted row, rstd);
+    shift fp32 [rows] (the producer's ln_out shift) is advanced to the row's true mean."""
+    _require_cuda(stat, out, shift)
     assert stat.dtype == torch.float32 and stat.is_contiguous() and stat.dim() == 3 and stat.shape[2] == 2
     assert out.dtype == torch.float32 and out.is_contiguous() and out.shape == (stat.shape[1], 2)
+    if shift is not None:
+        assert shift.dtype == torch.float32 and shift.is_contiguous() and shift.numel() >= stat.shape[1]
     with _timed("ln_row_stats", bytes=stat.numel() * 4 + out.numel() * 4):
-        check(lib().vf_ln_row_stats(stat.data_ptr(), stat.shape[0], stat.shape[1], stat.shape[1], D, float(eps),
-                                    out.data_ptr(), _stream()), "vf_ln_row_stats")
+        check(lib().vf_ln_row_stats(stat.data_ptr(), stat.shape[0], stat.shape[1], stat.shape[1], D, float(eps), int(variant),
+                                    out.data_ptr(), _p(shift), _stream()), "vf_ln_row_stats")
     return out
 
 
-def patch_embed(pixels, weight2d, bias, pos, out, P, tp, out_rows_per_sample, out_row_off, ln_out=None):
-    """pixels bf16 [B,C,T,H,W]; weight2d bf16 [N, C*tp*P*P]; out fp32 [rows, N] (see vfuse.h).
-    ln_out = (xb bf16 [rows, N], stat fp32 [N/32, rows, 2]): also emit the folded-LayerNorm producer outputs."""
+def patch_embed(pixels, weight2d, bias, pos, out, P, tp, out_rows_per_sample, out_row_off):
+    """pixels bf16 [B,C,T,H,W]; weight2d bf16 [N, C*tp*P*P]; out fp32 [rows, N] (see vfuse.h)."""
     _require_cuda(pixels, weight2d, out)
     assert pixels.dtype == torch.bfloat16 and pixels.is_contiguous() and pixels.dim() == 5
     B, Cc, T, H, W = pixels.shape
     N = weight2d.shape[0]
-    xb_p = xb_ld = st_p = st_ld = fl_p = 0
-    if ln_out is not None:
-        xb, stat = ln_out[:2]
-        if len(ln_out) > 2:
-            _require_cuda(ln_out[2])
-            assert ln_out[2].dtype == torch.int32 and ln_out[2].is_contiguous()
-            fl_p = ln_out[2].data_ptr()
-        _require_cuda(xb, stat)
-        assert xb.dtype == torch.bfloat16 and xb.stride(-1) == 1 and stat.dtype == torch.float32 and stat.is_contiguous()
-        assert stat.dim() == 3 and stat.shape[0] == N // 32 and stat.shape[2] == 2
-        xb_p, xb_ld, st_p, st_ld = xb.data_ptr(), xb.stride(-2), stat.data_ptr(), stat.shape[1]
     with _timed("patch_embed", flops=2.0 * B * (T // tp) * (H // P) * (W // P) * N * weight2d.shape[1]):
         check(
-            lib().vf_patch_embed_ln(pixels.data_ptr(), B, Cc, T, H, W, P, tp, weight2d.data_ptr(), _p(bias), _p(pos),
-                                    pos.stride(0) if pos is not None else 0, N, out.data_ptr(), out.stride(-2),
-                                    out_rows_per_sample, out_row_off, xb_p, xb_ld, st_p, st_ld, fl_p, _stream()),
-            "vf_patch_embed_ln",
+            lib().vf_patch_embed(pixels.data_ptr(), B, Cc, T, H, W, P, tp, weight2d.data_ptr(), _p(bias), _p(pos),
+                                 pos.stride(0) if pos is not None else 0, N, out.data_ptr(), out.stride(-2),
+                                 out_rows_per_sample, out_row_off, _stream()),
+            "vf_patch_embed",
         )
     return out
 
 
-def attention(qkv, out, B, S, H, scale):
+def attention(qkv, out, B, S, H, scale, head_dim=64):
     _require_cuda(qkv, out)
     assert qkv.dtype == torch.bfloat16 and qkv.is_contiguous() and out.dtype == torch.bfloat16 and out.is_contiguous()
-    assert qkv.numel() == B * S * 3 * H * 64 and out.numel() == B * S * H * 64
-    with _timed("attention", flops=4.0 * B * H * S * S * 64):
-        check(lib().vf_attention_fwd(qkv.data_ptr(), out.data_ptr(), B, S, H, float(scale), _stream()),
-              "vf_attention_fwd")
+    assert qkv.numel() == B * S * 3 * H * head_dim and out.numel() == B * S * H * head_dim
+    with _timed("attention", flops=4.0 * B * H * S * S * head_dim):
+        check(lib().vf_attention_fwd_hd(qkv.data_ptr(), out.data_ptr(), B, S, H, head_dim, float(scale), _stream()),
+              "vf_attention_fwd_hd")
     return out
 
 
@@ -343,14 +325,17 @@ def attention_gqa(q2d, k2d, v2d, out2d, B, S, Hq, Hkv, scale, causal=True, q_col
     return out2d
 
 
-def layernorm(x2d, w, b, out, eps, variant=0, merge=1, nh=0, nw=0):
-    _require_cuda(x2d, w, b, out)
+def layernorm(x2d, w, b, out, eps, variant=0, merge=1, nh=0, nw=0, mean_out=None):
+    _require_cuda(x2d, w, b, out, mean_out)
     rows, D = x2d.shape
     assert x2d.stride(1) == 1 and out.is_contiguous()
+    if mean_out is not None:
+        assert mean_out.dtype == torch.float32 and mean_out.is_contiguous() and mean_out.numel() >= rows
     with _timed("layernorm", bytes=float(rows * D * (x2d.element_size() + out.element_size()))):
         check(
             lib().vf_layernorm(x2d.data_ptr(), _DT[x2d.dtype], x2d.stride(0), w.data_ptr(), b.data_ptr(),
-                               out.data_ptr(), _DT[out.dtype], rows, D, float(eps), variant, merge, nh, nw, _stream()),
+                               out.data_ptr(), _DT[out.dtype], rows, D, float(eps), variant, merge, nh, nw, _p(mean_out),
+                               _stream()),
             "vf_layernorm",
         )
     return out
@@ -506,4 +491,72 @@ def preprocess_u8(img_u8, mean, std, T=2, dtype=torch.bfloat16):
     with _timed("preprocess_u8", bytes=float(B * H * W * 3 * (1 + T * out.element_size()))):
         check(lib().vf_preprocess_u8(img_u8.data_ptr(), B, H, W, T, m3, s3, out.data_ptr(), _DT[dtype], _stream()),
               "vf_preprocess_u8")
+    return out
+
+
+def gelu(x, tanh_form=False):
+    """Stand-alone GELU (erf form by default, tanh form for nn.GELU(approximate="tanh")); fp32 or bf16, any shape."""
+    _require_cuda(x)
+    if x.dtype not in _DT:
+        raise VFuseError(f"vf_gelu handles fp32 and bf16 tensors, got {x.dtype}")
+    xc = x.contiguous()
+    out = torch.empty_like(xc)
+    if xc.numel() == 0:
+        return out
+    with _timed("gelu", bytes=2.0 * xc.numel() * xc.element_size()):
+        check(lib().vf_gelu(xc.data_ptr(), out.data_ptr(), _DT[xc.dtype], xc.numel(), int(bool(tanh_form)), _stream()), "vf_gelu")
+    return out
+
+
+def rmsnorm_zc(x, one_plus_scale, eps):
+    """ZeroCenteredRMSNorm.forward over the last dim; x fp32 or bf16, one_plus_scale fp32 [D]."""
+    _require_cuda(x, one_plus_scale)
+    if x.dtype not in _DT:
+        raise VFuseError(f"vf_rmsnorm_zc handles fp32 and bf16 tensors, got {x.dtype}")
+    D = x.shape[-1]
+    x2d = x.reshape(-1, D)
+    if x2d.stride(1) != 1:
+        x2d = x2d.contiguous()
+    out = torch.empty((x2d.shape[0], D), dtype=x.dtype, device=x.device)
+    assert one_plus_scale.dtype == torch.float32 and one_plus_scale.is_contiguous() and one_plus_scale.numel() == D
+    with _timed("rmsnorm_zc", bytes=2.0 * x2d.numel() * x2d.element_size()):
+        check(lib().vf_rmsnorm_zc(x2d.data_ptr(), x2d.stride(0), one_plus_scale.data_ptr(), out.data_ptr(), D, _DT[x.dtype],
+                                  x2d.shape[0], D, float(eps), _stream()), "vf_rmsnorm_zc")
+    return out.view(x.shape)
+
+
+def embed_pos_concat(input_ids, tok_table, pos_table, fused, row_off):
+    """fused fp32 [b, n_total, D]: fused[:, row_off:row_off+seq] = tok_table[input_ids] + pos_table[:seq]."""
+    _require_cuda(input_ids, tok_table, pos_table, fused)
+    b, seq = input_ids.shape
+    ids = input_ids.to(torch.int64).contiguous()
+    assert tok_table.dtype == pos_table.dtype and tok_table.dtype in _DT and tok_table.is_contiguous() and pos_table.is_contiguous()
+    assert fused.dtype == torch.float32 and fused.is_contiguous() and fused.dim() == 3 and fused.shape[0] == b
+    D = tok_table.shape[1]
+    assert fused.shape[2] == D and pos_table.shape[1] == D
+    with _timed("embed_pos_concat", bytes=float(b * seq * D * (2 * tok_table.element_size() + 4))):
+        check(lib().vf_embed_pos_concat(ids.data_ptr(), tok_table.data_ptr(), tok_table.shape[0], pos_table.data_ptr(),
+                                        pos_table.shape[0], _DT[tok_table.dtype], fused.data_ptr(), b, seq, D, fused.shape[1],
+                                        int(row_off), _stream()), "vf_embed_pos_concat")
+    return fused
+
+
+def im2col_patches(x, P):
+    """x [B, C, H, W] fp32/bf16 -> bf16 [B*nh*nw, C*P*P (padded to a multiple of 8)] patch rows, columns (c, py, px)."""
+    _require_cuda(x)
+    assert x.dim() == 4 and x.is_contiguous() and x.dtype in _DT
+    B, Cc, H, W = x.shape
+    K = Cc * P * P
+    ld = (K + 7) // 8 * 8
+    out = torch.zeros((B * (H // P) * (W // P), ld), dtype=torch.bfloat16, device=x.device) if ld != K else \
+        torch.empty((B * (H // P) * (W // P), ld), dtype=torch.bfloat16, device=x.device)
+    with _timed("im2col", bytes=float(x.numel() * (x.element_size() + 2))):
+        check(lib().vf_im2col_patches(x.data_ptr(), _DT[x.dtype], B, Cc, H, W, P, out.data_ptr(), ld, _stream()), "vf_im2col_patches")
+    return out[:, :K] if ld != K else out
+
+
+def fill_rows(src, out, B, rows_per_sample, D, add_row0=None):
+    _require_cuda(src, out, add_row0)
+    assert src.dtype == torch.float32 and src.is_contiguous() and out.dtype == torch.float32 and out.is_contiguous()
+    check(lib().vf_fill_rows_f32(src.data_ptr(), _p(add_row0), out.data_ptr(), B, rows_per_sample, D, _stream()), "vf_fill_rows_f32")
     return out

@@ -42,15 +42,15 @@ bool pdl_enabled() {
 }
 
 int device_sm_count() {
-  static int sms = -1;
-  if (sms < 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
-    int n = 0;
+  static std::atomic<int> sms[64];   // zero-initialised; indexed by device ordinal
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  int n = sms[dev & 63].load(std::memory_order_relaxed);
+  if (n == 0) {
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
-    sms = n;
+    sms[dev & 63].store(n, std::memory_order_relaxed);
   }
-  return sms;
+  return n;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,

@@ -637,15 +637,24 @@ extern "C" int vf_attention_fwd(const void* qkv, void* out, int32_t B, int32_t S
   p.trace_n = g_trace_n;
   using kern_t = void (*)(const AttnParams, const CUtensorMap, const CUtensorMap);
   static const kern_t kerns[2] = {attention_kernel<0>, attention_kernel<ATT_TRACE>};
-  static bool configured[2] = {false, false};
-  if (!configured[flags]) {
-    VF_CUDA(cudaFuncSetAttribute(kerns[flags], cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem::TOTAL));
-    configured[flags] = true;
-  }
+  static std::atomic<uint64_t> configured[2];
+  if (int e2 = ensure_dynamic_smem(kerns[flags], AttnSmem::TOTAL, configured[flags])) return e2;
   const int grid = p.n_items < sms ? p.n_items : sms;
   VF_CUDA(launch_pdl(kerns[flags], dim3(grid), dim3(ATT_THREADS), AttnSmem::TOTAL, static_cast<cudaStream_t>(stream), 1, p,
                      tmQ, tmKV));
   count_launch();
   VF_CUDA(cudaGetLastError());
   return VF_OK;
+}
+
+int vf_attention_small_launch(const void* qkv, void* out, int B, int S, int H, int hd, float scale, cudaStream_t stream);
+
+extern "C" int vf_attention_fwd_hd(const void* qkv, void* out, int32_t B, int32_t S, int32_t H, int32_t head_dim, float scale,
+                                   void* stream) {
+  if (head_dim == 64) return vf_attention_fwd(qkv, out, B, S, H, scale, stream);
+  VF_REQUIRE(qkv && out, VF_ERR_ARG, "vf_attention_fwd_hd: null pointer");
+  VF_REQUIRE(B > 0 && S > 0 && H > 0 && head_dim > 0, VF_ERR_ARG, "vf_attention_fwd_hd: bad shape B=%d S=%d H=%d hd=%d", B, S, H, head_dim);
+  VF_REQUIRE((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0, VF_ERR_ALIGN,
+             "vf_attention_fwd_hd: pointers must be 16-byte aligned");
+  return vf_attention_small_launch(qkv, out, B, S, H, head_dim, scale, static_cast<cudaStream_t>(stream));
 }

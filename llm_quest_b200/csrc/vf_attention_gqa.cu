@@ -480,11 +480,8 @@ extern "C" int vf_attention_gqa_fwd(const void* q, int64_t ldq, int32_t q_col0, 
   const int sms = device_sm_count();
   VF_REQUIRE(sms > 0, VF_ERR_NO_DEVICE, "no CUDA device");
   const int grid = p.n_items < sms ? p.n_items : sms;
-  static bool configured = false;
-  if (!configured) {
-    VF_CUDA(cudaFuncSetAttribute(attention_gqa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GqaSmem::TOTAL));
-    configured = true;
-  }
+  static std::atomic<uint64_t> configured{0};
+  if (int e2 = ensure_dynamic_smem(attention_gqa_kernel, GqaSmem::TOTAL, configured)) return e2;
   attention_gqa_kernel<<<grid, G_THREADS, GqaSmem::TOTAL, static_cast<cudaStream_t>(stream)>>>(p, tmQ, tmK, tmV);
   count_launch();
   VF_CUDA(cudaGetLastError());

@@ -13,6 +13,9 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <atomic>
+#include <type_traits>
+
 #include "../../include/vfuse.h"  // VF_OK / VF_ERR_* codes and the exported prototypes
 
 #if defined(__CUDA_ARCH__) && !defined(__CUDA_ARCH_FEAT_SM100_ALL)
@@ -47,7 +50,21 @@ int encode_tmap(CUtensorMap* out, CUtensorMapDataType dt, uint32_t rank, const v
                 const uint64_t* dims, const uint64_t* strides_bytes /* rank-1 entries */,
                 const uint32_t* box, CUtensorMapSwizzle swz);
 
-int device_sm_count();
+int device_sm_count();   // of the CURRENT device (a process may drive several)
+
+// One-time opt-in of `kernel` to `bytes` of dynamic shared memory on the current device. The attribute is per
+// (function, device), so the "done" mask carries one bit per device ordinal; safe from several host threads.
+template <typename Kernel>
+inline int ensure_dynamic_smem(Kernel kernel, int bytes, std::atomic<uint64_t>& done) {
+  int dev = 0;
+  VF_CUDA(cudaGetDevice(&dev));
+  const uint64_t bit = 1ull << (dev & 63);
+  if (!(done.load(std::memory_order_acquire) & bit)) {
+    VF_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    done.fetch_or(bit, std::memory_order_release);
+  }
+  return 0;
+}
 void count_launch();  // bumps the counter behind vf_launch_count()
 bool pdl_enabled();   // programmatic dependent launch between consecutive libvfuse kernels (opt-in: VF_PDL=1)
 

@@ -31,6 +31,7 @@
 
 #include <math.h>
 #include <stdlib.h>
+#include <atomic>
 #include <type_traits>
 
 namespace vf {
@@ -74,19 +75,14 @@ struct GemmParams {
   int Tp, T, C, tp, P; // frames after temporal merge, raw frames, channels, temporal patch, patch
   const float* pos;
   long long ld_pos;
+  int peer_mc;         // peer[0] is an NVSwitch multicast (multimem) address: stores go through multimem.st
   // LayerNorm folded into the neighbouring GEMMs (see vf_epilogue in vfuse.h)
-  __nv_bfloat16* ln_xb;      // producer: bf16 copy of the fp32 output rows
+  __nv_bfloat16* ln_xb;      // producer: bf16 copy of the fp32 output rows, minus the row's shift
   long long ln_ldxb;
-  float2* ln_stat_out;       // producer: [N/32][ln_stat_ld] partial (sum, sum of squares)
+  float2* ln_stat_out;       // producer: [N/32][ln_stat_ld] partial (sum, sum of squares) of the shifted rows
   long long ln_stat_ld;
-  float2* ln_rows_out;       // producer: [M] (mean, rstd), written by the warp that completes a 32-row group
-  int* ln_counters;          // producer: [ceil(M/32)] contribution counters, zero before and after every launch
-  int ln_contribs;           // contributions per 32-row group = N / columns per epilogue warp
-  float ln_eps;
-  const float2* ln_row_stats;  // consumer: [M] (mean, rstd); with ln_part_in it is the buffer the publishing warps fill
-  const float2* ln_part_in;    // consumer: [K/32][ln_stat_ld] partial sums of the producer (NULL: ln_row_stats is final)
-  int* ln_flags;               // [1] number of consumer epilogue warps that finished their share of the statistics:
-                               // cleared by the producer launch, counted up and polled by the consumer launch
+  const float* ln_shift;     // producer: [M] per-row shift (an estimate of the row mean) or nullptr
+  const float2* ln_row_stats;  // consumer: [M] (mean of the shifted row, rstd)
   const float* ln_colsum;      // consumer: [N]
 };
 
@@ -332,90 +328,15 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
                    : "memory");
     };
 
-    // Folded LayerNorm, consumer side. (mean, rstd) per row are either final already (a vf_ln_row_stats launch in
-    // between) or — ln_part_in — finished by THIS launch: before their first tile the epilogue warps of the whole grid
-    // add up the producer's K/32 partial sums, one 32-row group per warp and round (9.6 MB at cfg-2, hidden behind the
-    // first tile's main loop), and count themselves in; the first epilogue waits until every warp of the grid has.
-    // Deadlock-free: the grid is persistent (every CTA resident); the producer GEMM cleared the counter.
-    [[maybe_unused]] bool ln_ready = p.ln_part_in == nullptr;
-    if constexpr (EPI == VF_EPI_GELU_TANH_BF16 || EPI == VF_EPI_GELU_ERF_BF16 || EPI == VF_EPI_QKV_ROPE_BF16) {
-      if (p.ln_part_in != nullptr) {
-        float2* rows = const_cast<float2*>(p.ln_row_stats);
-        const int parts = p.K >> 5, groups = (p.M + 31) >> 5;
-        const float inv_d = 1.0f / static_cast<float>(p.K);
-        for (int g = blockIdx.x * EpiCfg<EPI>::WARPS + (warp - 2); g < groups; g += gridDim.x * EpiCfg<EPI>::WARPS) {
-          const int row = g * 32 + lane;
-          if (row < p.M) {
-            const float2* sp = p.ln_part_in + row;
-            float s_ = 0.f, q_ = 0.f;
-#pragma unroll 8
-            for (int j = 0; j < parts; ++j) {
-              const float2 t = __ldcg(sp + (long long)j * p.ln_stat_ld);
-              s_ += t.x; q_ += t.y;
-            }
-            const float mu = s_ * inv_d;
-            rows[row] = make_float2(mu, rsqrtf(fmaxf(fmaf(-mu, mu, q_ * inv_d), 0.f) + p.ln_eps));
-          }
-        }
-        __threadfence();
-        __syncwarp();
-        if (lane == 0) atomicAdd(p.ln_flags, 1);
-      }
-    }
+    // Folded LayerNorm, consumer side: (mean, rstd) per row are final when the launch starts (vf_ln_row_stats between the
+    // producing and the consuming GEMM); lane L fetches the pair of tile row L.
     [[maybe_unused]] auto ln_fetch = [&](int row_first, float& mu, float& rs) {
       mu = 0.f; rs = 0.f;
-      if (!ln_ready) {
-        if (lane == 0) {
-          const int want = gridDim.x * EpiCfg<EPI>::WARPS;
-          int v = 0;
-          const long long t0 = clock64();
-          while (true) {
-            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p.ln_flags) : "memory");
-            if (v >= want) break;
-            if (clock64() - t0 > 4000000000LL) {
-              printf("vf_gemm: LayerNorm row statistics incomplete (block %d: %d of %d warps)\n", blockIdx.x, v, want);
-              __trap();
-            }
-            __nanosleep(100);
-          }
-        }
-        __syncwarp();
-        ln_ready = true;
-      }
       const int row = row_first + lane;
       if (row < p.M) {
-        const float2 t = __ldcg(p.ln_row_stats + row);   // written during this launch in the ln_part_in mode: no .nc path
+        const float2 t = __ldg(p.ln_row_stats + row);
         mu = t.x; rs = t.y;
       }
-    };
-
-    // Folded LayerNorm, producer side: once a warp has stored its partial sums of a tile it counts itself in; the warp
-    // that completes a 32-row group (all N/32 partials present) turns them into (mean, rstd) right away — no separate
-    // kernel between the two GEMMs, no atomics on the data, fixed summation order (j = 0, 1, ...).
-    [[maybe_unused]] auto ln_finalize = [&](int row_first) {
-      if (p.ln_rows_out == nullptr || row_first >= p.M) return;
-      __threadfence();                       // this warp's partial sums are visible device-wide
-      __syncwarp();
-      int old = 0;
-      if (lane == 0) old = atomicAdd(p.ln_counters + (row_first >> 5), 1);
-      old = __shfl_sync(0xffffffffu, old, 0);
-      if (old != p.ln_contribs - 1) return;
-      __threadfence();                       // ... and everybody else's are visible to this warp
-      const int row = row_first + lane;
-      if (row < p.M) {
-        const float2* sp = p.ln_stat_out + row;
-        const int parts = p.N >> 5;
-        const float inv_d = 1.0f / static_cast<float>(p.N);
-        float s_ = 0.f, q_ = 0.f;
-#pragma unroll 8
-        for (int j = 0; j < parts; ++j) {
-          const float2 t = __ldcg(sp + (long long)j * p.ln_stat_ld);
-          s_ += t.x; q_ += t.y;
-        }
-        const float mu = s_ * inv_d;
-        p.ln_rows_out[row] = make_float2(mu, rsqrtf(fmaxf(fmaf(-mu, mu, q_ * inv_d), 0.f) + p.ln_eps));
-      }
-      if (lane == 0) p.ln_counters[row_first >> 5] = 0;   // ready for the next launch
     };
 
     // Residual epilogue: the fp32 residual slab of a tile (128 KB) is pulled into L2 one tile ahead, while
@@ -473,8 +394,8 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
           const int col0 = (tile % p.num_n_blk) * BN + chalf * COLS_PER_WARP;
           const int row0 = ((tile / p.num_n_blk) * CG + rank) * BM + quarter * 32;
           prefetch_res(tile + tile_step);
-          if (p.ln_flags && ln_out && (tile % p.num_n_blk) == 0 && chalf == 0 && lane == 0)
-            p.ln_flags[0] = 0;                     // the consumer's "statistics done" counter starts from zero
+          // folded-LayerNorm producer: the bf16 copy and the partial sums are taken of x - shift[row] (thread = row)
+          const float sh = (ln_out && p.ln_shift && row0 + lane < p.M) ? __ldg(p.ln_shift + row0 + lane) : 0.f;
           const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + chalf * COLS_PER_WARP;
 #pragma unroll 1
           for (int c = 0; c < COLS_PER_WARP / 32; ++c) {
@@ -531,6 +452,7 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
               for (int j = 0; j < 8; ++j) {
                 // same association as the staged epilogue (4-column shares added in column order): a row's statistics
                 // must not depend on which of the two paths its batch size selects
+                x[j].x -= sh; x[j].y -= sh; x[j].z -= sh; x[j].w -= sh;
                 s_ += (x[j].x + x[j].y) + (x[j].z + x[j].w);
                 q_ += fmaf(x[j].x, x[j].x, fmaf(x[j].y, x[j].y, fmaf(x[j].z, x[j].z, x[j].w * x[j].w)));
               }
@@ -552,7 +474,6 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
               p.ln_stat_out[(long long)(col >> 5) * p.ln_stat_ld + row0 + lane] = make_float2(s_, q_);
             if (++slot == R) { slot = 0; ph ^= 1; }
           }
-          if (ln_out) ln_finalize(row0);
           if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
         if (lane == 0) tma_store_wait<0>();
@@ -662,11 +583,6 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
           const int tpr = t % p.Tp;
           const int b = t / p.Tp;
           const long long base = (long long)b * p.grp_stride + p.row_off + (long long)tpr * p.nh * p.nw;
-          {
-            const int rq = quarter * 32 + lane;
-            const int ph = phb * 16 + (rq >> 3), pw = pwb * 8 + (rq & 7);
-            if (ph < p.nh && pw < p.nw) lane_orow = base + ph * p.nw + pw;
-          }
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int r_local = r0 + 4 * i;          // tile rows are a 16 x 8 rectangle of patches
@@ -716,6 +632,11 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
         }
       };
       load_res(0);
+      [[maybe_unused]] float shv[8];
+      if constexpr (EPI == VF_EPI_BIAS_RES_F32 && !PATCH) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) shv[i] = (p.ln_xb && p.ln_shift && orow[i] >= 0) ? __ldg(p.ln_shift + orow[i]) : 0.f;
+      }
 
       // LayerNorm folded into this GEMM (consumer side): lane L fetches (mean, rstd) of tile row quarter*32 + L while the
       // tensor pipe is still busy with the tile; the coalesced mapping below gets the values of its rows by shuffle.
@@ -854,14 +775,18 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
                 }
                 if constexpr (EPI == VF_EPI_BIAS_RES_F32 || PATCH) {
                   v[0] += ex[i].x; v[1] += ex[i].y; v[2] += ex[i].z; v[3] += ex[i].w;
+                }
+                if constexpr (EPI == VF_EPI_BIAS_RES_F32 && !PATCH) {
                   if (ln_out) {
-                    // producer side of the folded LayerNorm: bf16 copy of the row (the next GEMM's A operand), and this
-                    // lane's share of the row's (sum, sum of squares) parked in the staging slot it has just read
-                    write_staged2(stA, rl + 4 * i, (v[0] + v[1]) + (v[2] + v[3]),
-                                  fmaf(v[0], v[0], fmaf(v[1], v[1], fmaf(v[2], v[2], v[3] * v[3]))));
+                    // producer side of the folded LayerNorm: bf16 copy of the row minus its shift (the next GEMM's A
+                    // operand), and this lane's share of the shifted row's (sum, sum of squares) parked in the staging slot
+                    // it has just read
+                    const float u[4] = {v[0] - shv[i], v[1] - shv[i], v[2] - shv[i], v[3] - shv[i]};
+                    write_staged2(stA, rl + 4 * i, (u[0] + u[1]) + (u[2] + u[3]),
+                                  fmaf(u[0], u[0], fmaf(u[1], u[1], fmaf(u[2], u[2], u[3] * u[3]))));
                     if (!decltype(guarded)::value || orow[i] >= 0)
                       *reinterpret_cast<uint2*>(p.ln_xb + orow[i] * p.ln_ldxb + cc) =
-                          make_uint2(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]));
+                          make_uint2(pack_bf16(u[0], u[1]), pack_bf16(u[2], u[3]));
                   }
                 }
                 if constexpr (EPI == VF_EPI_GELU_TANH_BF16) {
@@ -876,6 +801,19 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
                   if constexpr (EPI == VF_EPI_BIAS_BF16 || EPI == VF_EPI_BIAS_F32) {
                     if (p.n_peers > 0) {   // fused all-gather: the same element to every GPU's copy of the gathered buffer
                       const long long off = (obase[i] - reinterpret_cast<char*>(p.out)) + (long long)cc * ESZ;
+                      if (p.peer_mc) {
+                        // NVSwitch multicast mapping: only multimem.* may touch it; the switch replicates the store
+                        // into every GPU's copy of the gathered buffer
+                        if constexpr (OUT_F32)
+                          asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p.peer[0] + off), "f"(v[0]),
+                                       "f"(v[1]), "f"(v[2]), "f"(v[3])
+                                       : "memory");
+                        else
+                          asm volatile("multimem.st.weak.global.v2.bf16x2 [%0], {%1, %2};" ::"l"(p.peer[0] + off),
+                                       "r"(pack_bf16(v[0], v[1])), "r"(pack_bf16(v[2], v[3]))
+                                       : "memory");
+                        continue;
+                      }
                       for (int r = 0; r < p.n_peers; ++r) {
                         if constexpr (OUT_F32)
                           *reinterpret_cast<float4*>(p.peer[r] + off) = make_float4(v[0], v[1], v[2], v[3]);
@@ -894,7 +832,7 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
             };
             if (rows_all_valid) do_rows(std::false_type{});
             else do_rows(std::true_type{});
-            if constexpr (EPI == VF_EPI_BIAS_RES_F32 || PATCH) {
+            if constexpr (EPI == VF_EPI_BIAS_RES_F32 && !PATCH) {
               if (ln_out) {
                 // lane L adds up the 8 shares of tile row quarter*32 + L (no shuffles, no extra live registers) and the
                 // warp stores the 32 partial sums of this 32-column block with one coalesced 256-byte store
@@ -909,10 +847,7 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
                                : "memory");
                   s_ += a_; q_ += b_;
                 }
-                if (lane_orow >= 0) {
-                  p.ln_stat_out[(long long)(cc >> 5) * p.ln_stat_ld + lane_orow] = make_float2(s_, q_);
-                  if (p.ln_flags && cc < 32 && lane == 0) p.ln_flags[0] = 0;   // the consumer's "statistics done" counter
-                }
+                if (lane_orow >= 0) p.ln_stat_out[(long long)(cc >> 5) * p.ln_stat_ld + lane_orow] = make_float2(s_, q_);
               }
             }
             if (c + 1 < COLS_PER_WARP / 32) load_res(c + 1);
@@ -945,9 +880,6 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
         if (CG == 2) mbar_arrive_leader(&tempty_bar[acc]);   // the leader's MMA warp reuses the buffer pair-wide
         else mbar_arrive(&tempty_bar[acc]);
       }
-      if constexpr (EPI == VF_EPI_BIAS_RES_F32 && !PATCH) {   // after the release: the fence inside must not stall the MMA warp
-        if (p.ln_xb != nullptr && p.grp_rows == 0) ln_finalize(m_blk * BM + quarter * 32);
-      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
@@ -971,12 +903,9 @@ static int launch_gemm(const GemmParams& p, const CUtensorMap& tmA, const CUtens
   using L = SmemLayout<BN, CG, RING>;
   static const EpiMaps no_maps{};
   const EpiMaps& em = em_in ? *em_in : no_maps;
-  static bool configured = false;
   auto kfn = gemm_kernel<EPI, BN, PATCH, CG, RING>;
-  if (!configured) {
-    VF_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
-    configured = true;
-  }
+  static std::atomic<uint64_t> configured{0};
+  if (int e = ensure_dynamic_smem(kfn, L::TOTAL, configured)) return e;
   const int sms = device_sm_count();
   VF_REQUIRE(sms > 0, VF_ERR_NO_DEVICE, "no CUDA device");
   const int tiles = ((p.num_m_blk + CG - 1) / CG) * p.num_n_blk;
@@ -1075,6 +1004,8 @@ extern "C" int vf_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t l
       p.peer[i] = reinterpret_cast<char*>(ep->peer_out[i]);
     }
     p.n_peers = ep->n_peers;
+    p.peer_mc = ep->peer_multicast ? 1 : 0;
+    VF_REQUIRE(!p.peer_mc || p.n_peers == 1, VF_ERR_ARG, "vf_gemm_bf16: a multicast destination is ONE address (n_peers == 1)");
   }
 
   if (ep->ln_xb_out || ep->ln_stat_out) {
@@ -1090,43 +1021,24 @@ extern "C" int vf_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t l
     p.ln_ldxb = ep->ln_ldxb;
     p.ln_stat_out = static_cast<float2*>(ep->ln_stat_out);
     p.ln_stat_ld = ep->ln_stat_ld;
-    p.ln_flags = static_cast<int*>(ep->ln_flags);
-    if (ep->ln_rows_out) {
-      VF_REQUIRE(ep->ln_counters && (N % (bn / 2)) == 0 && (reinterpret_cast<uintptr_t>(ep->ln_rows_out) & 7) == 0, VF_ERR_ARG,
-                 "vf_gemm_bf16: ln_rows_out needs ln_counters and N %% %d == 0", bn / 2);
-      p.ln_rows_out = static_cast<float2*>(ep->ln_rows_out);
-      p.ln_counters = static_cast<int*>(ep->ln_counters);
-      p.ln_contribs = N / (bn / 2);
-      p.ln_eps = ep->ln_eps;
-    }
+    p.ln_shift = ep->ln_shift;
+    VF_REQUIRE((reinterpret_cast<uintptr_t>(ep->ln_shift) & 3) == 0, VF_ERR_ALIGN, "vf_gemm_bf16: ln_shift must be 4-byte aligned");
   }
   if (ep->ln_row_stats) {
     VF_REQUIRE(ep->mode == VF_EPI_GELU_TANH_BF16 || ep->mode == VF_EPI_GELU_ERF_BF16 || ep->mode == VF_EPI_QKV_ROPE_BF16,
                VF_ERR_ARG, "vf_gemm_bf16: ln_row_stats needs a GELU or QKV+RoPE epilogue");
     VF_REQUIRE(ep->ln_colsum, VF_ERR_ARG, "vf_gemm_bf16: folded LayerNorm (consumer) needs ln_colsum");
-    VF_REQUIRE(vec_ok && (N & 3) == 0 && (reinterpret_cast<uintptr_t>(ep->ln_colsum) & 15) == 0 &&
+    // N % 32: every 32-column block of a tile is entirely inside or outside the matrix, so no lane of an epilogue warp
+    // leaves the block loop while the others still exchange (mean, rstd) by shuffle
+    VF_REQUIRE(vec_ok && (N % 32) == 0 && (reinterpret_cast<uintptr_t>(ep->ln_colsum) & 15) == 0 &&
                    (reinterpret_cast<uintptr_t>(ep->ln_row_stats) & 7) == 0,
-               VF_ERR_ALIGN, "vf_gemm_bf16: folded LayerNorm (consumer) needs aligned rows and N %% 4 == 0");
+               VF_ERR_ALIGN, "vf_gemm_bf16: folded LayerNorm (consumer) needs aligned rows and N %% 32 == 0");
     p.ln_row_stats = static_cast<const float2*>(ep->ln_row_stats);
     p.ln_colsum = ep->ln_colsum;
-    if (ep->ln_part_in) {
-      VF_REQUIRE(ep->ln_flags && (K % 32) == 0 && ep->ln_stat_ld >= M && (reinterpret_cast<uintptr_t>(ep->ln_part_in) & 7) == 0,
-                 VF_ERR_ARG, "vf_gemm_bf16: ln_part_in needs ln_flags, K %% 32 == 0 and ln_stat_ld >= M");
-      p.ln_part_in = static_cast<const float2*>(ep->ln_part_in);
-      p.ln_flags = static_cast<int*>(ep->ln_flags);
-      p.ln_stat_ld = ep->ln_stat_ld;
-      p.ln_eps = ep->ln_eps;
-    }
   }
 
-  // CTA pairs for every 256-wide problem with at least one full pair of row blocks per SM pair
-  // (VF_GEMM_CG=1 forces the single-CTA kernel: development A/B switch)
-  static int cg_env = -1;
-  if (cg_env < 0) {
-    const char* e_ = getenv("VF_GEMM_CG");
-    cg_env = e_ ? atoi(e_) : 2;
-  }
-  const int cg = (bn == 256 && cg_env == 2 && p.num_m_blk >= 2) ? 2 : 1;
+  // CTA pairs for every 256-wide problem with at least one full pair of row blocks
+  const int cg = (bn == 256 && p.num_m_blk >= 2) ? 2 : 1;
 
   CUtensorMap tmA, tmB;
   {
@@ -1146,19 +1058,11 @@ extern "C" int vf_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t l
     if (e) return e;
   }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  // TMA residual epilogue (VF_RES_TMA=0: the staged register epilogue, development A/B switch)
-  // The ring takes two of the six main-loop stages: it pays where the epilogue bounds the kernel (short K: proj) and costs
-  // where the main loop does (K=3072, cold operands: lin2 211 vs 189 us under ncu), hence the K limit (VF_RES_TMA_MAXK).
-  static int res_tma_env = -1, res_tma_maxk = 1024;
-  if (res_tma_env < 0) {
-    const char* e_ = getenv("VF_RES_TMA");
-    res_tma_env = e_ ? atoi(e_) : 1;
-    const char* k_ = getenv("VF_RES_TMA_MAXK");
-    if (k_) res_tma_maxk = atoi(k_);
-  }
+  // The TMA residual ring takes two of the six main-loop stages: it pays where the epilogue bounds the kernel (short K:
+  // proj, 96 -> 81 us) and costs where the main loop does (K = 3072, cold operands: lin2 240 vs 211 us in the step).
+  constexpr int kResTmaMaxK = 1024;
   EpiMaps em{};
-  if (cg == 2 && ep->mode == VF_EPI_BIAS_RES_F32 && ep->grp_rows <= 0 && vec_ok && (N % 32) == 0 && res_tma_env &&
-      K <= res_tma_maxk &&
+  if (cg == 2 && ep->mode == VF_EPI_BIAS_RES_F32 && ep->grp_rows <= 0 && vec_ok && (N % 32) == 0 && K <= kResTmaMaxK &&
       (!p.ln_xb || ((p.ln_ldxb % 8) == 0 && (reinterpret_cast<uintptr_t>(p.ln_xb) & 15) == 0))) {
     uint64_t dims[2] = {(uint64_t)N, (uint64_t)M};
     uint32_t box[2] = {32, 32};
@@ -1173,13 +1077,8 @@ extern "C" int vf_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t l
     }
     p.res_tma = 1;
   }
-  static int out_tma_env = -1;
-  if (out_tma_env < 0) {
-    const char* e_ = getenv("VF_OUT_TMA");
-    out_tma_env = e_ ? atoi(e_) : 1;
-  }
   if ((ep->mode == VF_EPI_BIAS_BF16 || ep->mode == VF_EPI_GELU_TANH_BF16 || ep->mode == VF_EPI_GELU_ERF_BF16) &&
-      ep->grp_rows <= 0 && p.n_peers == 0 && vec_ok && (N % 32) == 0 && out_tma_env) {
+      ep->grp_rows <= 0 && p.n_peers == 0 && vec_ok && (N % 32) == 0) {
     uint64_t dims[2] = {(uint64_t)N, (uint64_t)M};
     uint32_t box[2] = {32, 32};
     uint64_t so[1] = {(uint64_t)ep->ldo * 2};
@@ -1197,16 +1096,6 @@ extern "C" int vf_patch_embed(const void* pixels, int32_t B, int32_t C, int32_t 
                               const float* bias, const float* pos, int64_t ld_pos, int32_t N,
                               float* out, int64_t ldo, int64_t out_rows_per_sample,
                               int64_t out_row_off, void* stream) {
-  return vf_patch_embed_ln(pixels, B, C, T, H, W, P, tp, weight, bias, pos, ld_pos, N, out, ldo, out_rows_per_sample,
-                           out_row_off, nullptr, 0, nullptr, 0, nullptr, stream);
-}
-
-extern "C" int vf_patch_embed_ln(const void* pixels, int32_t B, int32_t C, int32_t T, int32_t H,
-                                 int32_t W, int32_t P, int32_t tp, const void* weight,
-                                 const float* bias, const float* pos, int64_t ld_pos, int32_t N,
-                                 float* out, int64_t ldo, int64_t out_rows_per_sample,
-                                 int64_t out_row_off, void* ln_xb_out, int64_t ln_ldxb, void* ln_stat_out,
-                                 int64_t ln_stat_ld, void* ln_flags, void* stream) {
   VF_REQUIRE(pixels && weight && out, VF_ERR_ARG, "vf_patch_embed: null pointer");
   VF_REQUIRE(B > 0 && C > 0 && T > 0 && H > 0 && W > 0 && N > 0, VF_ERR_ARG, "vf_patch_embed: bad shape");
   VF_REQUIRE(P == 16, VF_ERR_ARG,
@@ -1243,19 +1132,6 @@ extern "C" int vf_patch_embed_ln(const void* pixels, int32_t B, int32_t C, int32
   p.out = out; p.ldo = ldo;
   p.grp_stride = out_rows_per_sample; p.row_off = out_row_off;
   p.vec_ok = 1;
-  if (ln_xb_out || ln_stat_out) {
-    const int64_t rows = (int64_t)(B - 1) * out_rows_per_sample + out_row_off + (int64_t)Tp * nh * nw;
-    VF_REQUIRE(ln_xb_out && ln_stat_out && ln_stat_ld >= rows, VF_ERR_ARG,
-               "vf_patch_embed_ln: ln_xb_out, ln_stat_out and ln_stat_ld >= output rows go together");
-    VF_REQUIRE((N % 32) == 0 && ln_ldxb >= N && (ln_ldxb % 4) == 0 && (reinterpret_cast<uintptr_t>(ln_xb_out) & 7) == 0 &&
-                   (reinterpret_cast<uintptr_t>(ln_stat_out) & 7) == 0,
-               VF_ERR_ALIGN, "vf_patch_embed_ln: needs N %% 32 == 0 and aligned xb rows");
-    p.ln_xb = static_cast<__nv_bfloat16*>(ln_xb_out);
-    p.ln_ldxb = ln_ldxb;
-    p.ln_stat_out = static_cast<float2*>(ln_stat_out);
-    p.ln_stat_ld = ln_stat_ld;
-    p.ln_flags = static_cast<int*>(ln_flags);
-  }
 
   CUtensorMap tmA, tmB;
   {

@@ -44,7 +44,7 @@ template <typename TIn, typename TOut, int NV>
 __global__ void __launch_bounds__(LN_WARPS * 32)
 layernorm_kernel(const TIn* __restrict__ x, long long ldx, const float* __restrict__ w,
                  const float* __restrict__ b, TOut* __restrict__ out, long long rows, float eps,
-                 int variant, int merge, int nh, int nw) {
+                 int variant, int merge, int nh, int nw, float* __restrict__ mean_out) {
   constexpr int D = NV * 128;
   const int lane = threadIdx.x & 31;
   const long long row = static_cast<long long>(blockIdx.x) * LN_WARPS + (threadIdx.x >> 5);
@@ -61,6 +61,7 @@ layernorm_kernel(const TIn* __restrict__ x, long long ldx, const float* __restri
 #pragma unroll
   for (int g = 0; g < NV; ++g) s += (v[g][0] + v[g][1]) + (v[g][2] + v[g][3]);
   const float mean = warp_sum(s) * (1.0f / D);
+  if (mean_out != nullptr && lane == 0) mean_out[row] = mean;   // the folded-LayerNorm producers' first row shift
   float q = 0.f;
 #pragma unroll
   for (int g = 0; g < NV; ++g) {
@@ -101,14 +102,14 @@ layernorm_kernel(const TIn* __restrict__ x, long long ldx, const float* __restri
 template <typename TIn, typename TOut>
 static int launch_ln(const void* x, long long ldx, const float* w, const float* b, void* out,
                      long long rows, int D, float eps, int variant, int merge, int nh, int nw,
-                     cudaStream_t s) {
+                     float* mean_out, cudaStream_t s) {
   const unsigned grid = static_cast<unsigned>((rows + LN_WARPS - 1) / LN_WARPS);
   const TIn* xi = static_cast<const TIn*>(x);
   TOut* o = static_cast<TOut*>(out);
 #define VF_LN_CASE(NV)                                                                            \
   case NV:                                                                                        \
     VF_CUDA(launch_pdl(layernorm_kernel<TIn, TOut, NV>, dim3(grid), dim3(LN_WARPS * 32), 0, s, 1, xi, \
-                       static_cast<long long>(ldx), w, b, o, static_cast<long long>(rows), eps, variant, merge, nh, nw)); \
+                       static_cast<long long>(ldx), w, b, o, static_cast<long long>(rows), eps, variant, merge, nh, nw, mean_out)); \
     break;
   switch (D / 128) {
     VF_LN_CASE(1) VF_LN_CASE(2) VF_LN_CASE(3) VF_LN_CASE(4) VF_LN_CASE(6) VF_LN_CASE(8)
@@ -133,8 +134,8 @@ __global__ void vit_cls_pos_kernel(const float* __restrict__ cls, const float* _
 // One block = 32 rows x 8 groups of partials: thread (g, r) adds the partials j = g, g+8, ... of row r (coalesced 256-byte
 // rows of float2), the 8 group sums meet in shared memory and warp 0 adds them in fixed order.
 __global__ void __launch_bounds__(256) ln_row_stats_kernel(const float2* __restrict__ part, int parts, long long ld,
-                                                           long long rows, float inv_d, float eps,
-                                                           float2* __restrict__ out) {
+                                                           long long rows, float inv_d, float eps, int variant,
+                                                           float2* __restrict__ out, float* __restrict__ shift) {
   __shared__ float2 acc[8][32];
   pdl_wait();
   pdl_launch_dependents();
@@ -157,8 +158,10 @@ __global__ void __launch_bounds__(256) ln_row_stats_kernel(const float2* __restr
       s += acc[k][l].x;
       q += acc[k][l].y;
     }
-    const float mu = s * inv_d;
-    out[r] = make_float2(mu, rsqrtf(fmaxf(fmaf(-mu, mu, q * inv_d), 0.f) + eps));
+    const float mu = s * inv_d;   // mean of the SHIFTED row: the consumer GEMM multiplies the shifted bf16 copy
+    const float var = fmaxf(fmaf(-mu, mu, q * inv_d), 0.f);
+    out[r] = make_float2(mu, variant == 0 ? rsqrtf(var + eps) : 1.0f / (sqrtf(var) + eps));
+    if (shift != nullptr) shift[r] += mu;   // the row's true mean: what the next producer subtracts before rounding
   }
 }
 
@@ -167,14 +170,15 @@ __global__ void __launch_bounds__(256) ln_row_stats_kernel(const float2* __restr
 using namespace vf;
 
 extern "C" int vf_ln_row_stats(const void* partials, int32_t parts, int64_t ld, int64_t rows, int32_t D, float eps,
-                               void* out, void* stream) {
-  VF_REQUIRE(partials && out && parts > 0 && rows > 0 && D > 0 && ld >= rows, VF_ERR_ARG, "vf_ln_row_stats: bad arguments");
+                               int32_t variant, void* out, float* shift, void* stream) {
+  VF_REQUIRE(partials && out && parts > 0 && rows > 0 && D > 0 && ld >= rows && (variant == 0 || variant == 1), VF_ERR_ARG,
+             "vf_ln_row_stats: bad arguments");
   VF_REQUIRE((reinterpret_cast<uintptr_t>(partials) & 7) == 0 && (reinterpret_cast<uintptr_t>(out) & 7) == 0, VF_ERR_ALIGN,
              "vf_ln_row_stats: pointers must be 8-byte aligned");
   const unsigned grid = static_cast<unsigned>((rows + 31) / 32);
   VF_CUDA(launch_pdl(ln_row_stats_kernel, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream), 1,
                      static_cast<const float2*>(partials), (int)parts, (long long)ld, (long long)rows,
-                     1.0f / static_cast<float>(D), eps, static_cast<float2*>(out)));
+                     1.0f / static_cast<float>(D), eps, (int)variant, static_cast<float2*>(out), shift));
   count_launch();
   VF_CUDA(cudaGetLastError());
   return VF_OK;
@@ -183,7 +187,7 @@ extern "C" int vf_ln_row_stats(const void* partials, int32_t parts, int64_t ld, 
 extern "C" int vf_layernorm(const void* x, int32_t in_dtype, int64_t ldx, const float* w,
                             const float* b, void* out, int32_t out_dtype, int64_t rows, int32_t D,
                             float eps, int32_t variant, int32_t merge, int32_t nh, int32_t nw,
-                            void* stream) {
+                            float* mean_out, void* stream) {
   VF_REQUIRE(x && w && b && out, VF_ERR_ARG, "vf_layernorm: null pointer");
   VF_REQUIRE(rows > 0 && D > 0 && D % 128 == 0, VF_ERR_ARG, "vf_layernorm: rows=%lld D=%d (D must be a multiple of 128)",
              (long long)rows, D);
@@ -200,13 +204,13 @@ extern "C" int vf_layernorm(const void* x, int32_t in_dtype, int64_t ldx, const 
   }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (in_dtype == 0 && out_dtype == 1)
-    return launch_ln<float, __nv_bfloat16>(x, ldx, w, b, out, rows, D, eps, variant, merge, nh, nw, s);
+    return launch_ln<float, __nv_bfloat16>(x, ldx, w, b, out, rows, D, eps, variant, merge, nh, nw, mean_out, s);
   if (in_dtype == 0 && out_dtype == 0)
-    return launch_ln<float, float>(x, ldx, w, b, out, rows, D, eps, variant, merge, nh, nw, s);
+    return launch_ln<float, float>(x, ldx, w, b, out, rows, D, eps, variant, merge, nh, nw, mean_out, s);
   if (in_dtype == 1 && out_dtype == 1)
-    return launch_ln<__nv_bfloat16, __nv_bfloat16>(x, ldx, w, b, out, rows, D, eps, variant, merge, nh, nw, s);
+    return launch_ln<__nv_bfloat16, __nv_bfloat16>(x, ldx, w, b, out, rows, D, eps, variant, merge, nh, nw, mean_out, s);
   if (in_dtype == 1 && out_dtype == 0)
-    return launch_ln<__nv_bfloat16, float>(x, ldx, w, b, out, rows, D, eps, variant, merge, nh, nw, s);
+    return launch_ln<__nv_bfloat16, float>(x, ldx, w, b, out, rows, D, eps, variant, merge, nh, nw, mean_out, s);
   set_last_error("vf_layernorm: dtype codes must be 0 (fp32) or 1 (bf16)");
   return VF_ERR_ARG;
 }

@@ -47,13 +47,13 @@ class ViTMultiHeadAttention(nn.Module):
 
     def attend(self, h2d, B, S):
         """h2d bf16 [B*S, d_in] -> context bf16 [B*S, d_out]."""
-        if self.head_dim != 64:
-            raise VFuseError(f"the fused attention kernel is built for head_dim 64, got {self.head_dim}")
+        if self.head_dim % 8 != 0 or self.head_dim > 128:
+            raise VFuseError(f"vf_attention_fwd_hd takes head dims that are multiples of 8 up to 128, got {self.head_dim}")
         w, b = self.packed_qkv()
         qkv = torch.empty((B * S, 3 * self.d_out), dtype=torch.bfloat16, device=h2d.device)
         _lib.gemm(h2d, w, VF_EPI_BIAS_BF16, qkv, bias=b)
         ctx = torch.empty((B * S, self.d_out), dtype=torch.bfloat16, device=h2d.device)
-        _lib.attention(qkv, ctx, B, S, self.num_heads, self.att_scaling)
+        _lib.attention(qkv, ctx, B, S, self.num_heads, self.att_scaling, head_dim=self.head_dim)
         return ctx
 
     def forward(self, x):

@@ -7,7 +7,8 @@ signatures, ``state_dict`` keys (``pos_embedding``, ``patch_embedding.cls_token`
 
 conv2d patchify runs as the im2col-free TMA-gather GEMM (the 3-D kernel with T = tp = 1) whose
 epilogue adds bias and the positional embedding and writes token-major rows 1..N of every sample;
-row 0 (class token + pos[0]) is written by vf_vit_cls_pos.
+row 0 (class token + pos[0]) is written by vf_vit_cls_pos. Patch sizes other than 16 (TINY_VIT_CONFIG, config.py:175-186)
+go through vf_im2col_patches + the plain GEMM; head dims other than 64 through the CUDA-core attention kernel.
 """
 
 from __future__ import annotations
@@ -16,7 +17,7 @@ import torch
 import torch.nn as nn
 
 from ... import _lib
-from ..._lib import VF_EPI_BIAS_F32, VFuseError
+from ..._lib import VF_EPI_BIAS_F32, VF_EPI_BIAS_RES_F32, VFuseError
 from ...qwen.qwen3_5.qwen3_5_vision_model import _Packed, _f32, _forward_only_guard, _w_bf16
 from .vit_transformer_block import LayerNorm, ViTTransformerBlock
 
@@ -51,9 +52,17 @@ class PatchEmbedding2D(nn.Module):
         out = torch.empty((B * S, D), dtype=torch.float32, device=x.device)
         if pos is None:
             pos = self._packed.get("zero_pos", [self.cls_token], lambda: torch.zeros((S, D), device=x.device))
-        px = _lib.to_bf16(x).unsqueeze(2)  # [B, C, 1, H, W]
-        _lib.patch_embed(px, w, bias, pos[1:], out, self.patch_size, 1, S, 1)
-        _lib.vit_cls_pos(cls, pos[0], out, B, S, D)
+        if self.patch_size == 16:
+            px = _lib.to_bf16(x).unsqueeze(2)  # [B, C, 1, H, W]
+            _lib.patch_embed(px, w, bias, pos[1:], out, self.patch_size, 1, S, 1)
+            _lib.vit_cls_pos(cls, pos[0], out, B, S, D)
+        else:
+            # other patch sizes (TINY_VIT_CONFIG: 4x4): patches unfolded to bf16 rows, every output row pre-filled with its
+            # position embedding (+ class token on row 0), then one GEMM accumulates conv + bias onto rows 1.. of each sample
+            xin = x.contiguous() if x.dtype in (torch.float32, torch.bfloat16) else x.float().contiguous()
+            rows = _lib.im2col_patches(xin, self.patch_size)
+            _lib.fill_rows(pos.contiguous(), out, B, S, D, add_row0=cls)
+            _lib.gemm(rows, w, VF_EPI_BIAS_RES_F32, out, bias=bias, res=out, grp_rows=self.num_patches, grp_stride=S, row_off=1)
         return out, B, S
 
     def forward(self, x):

@@ -43,17 +43,17 @@ class LayerNorm(nn.Module):
 
 
 class GELU(nn.Module):
-    """Exact (erf) GELU (reference :34-44). On the path it never runs on its own: FFN fuses it into
-    the lin1 GEMM epilogue (VF_EPI_GELU_ERF_BF16). Called directly it raises rather than silently
-    dispatching to an ATen kernel."""
+    """Exact (erf) GELU (reference :34-44): x * 0.5 * (1 + erf(x / sqrt 2)). Inside FFN it is the lin1 GEMM's epilogue
+    (VF_EPI_GELU_ERF_BF16); called on its own it is the vf_gelu kernel (fp32 or bf16, erff accuracy)."""
 
     def __init__(self):
         super().__init__()
 
     def forward(self, x):
-        raise _lib.VFuseError(
-            "GELU is fused into the lin1 GEMM epilogue (VF_EPI_GELU_ERF_BF16); call FFN / ViTTransformerBlock instead"
-        )
+        _forward_only_guard(self)
+        if x.dtype not in (torch.float32, torch.bfloat16):
+            return _lib.gelu(x.float()).to(x.dtype)
+        return _lib.gelu(x)
 
 
 class FFN(nn.Module):

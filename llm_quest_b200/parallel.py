@@ -111,16 +111,18 @@ class FusedAllGather:
         self.buf = symm.empty((slots, self.world * rows_local, cols), dtype=dtype, device=dev)
         self.hdl = symm.rendezvous(self.buf, self.group)
         self._ptrs = [int(p) for p in self.hdl.buffer_ptrs]
-        # NVSwitch multicast (NVLS): ONE store to the multicast address is replicated by the switch into every
+        # NVSwitch multicast (NVLS): ONE multimem.st to the multicast address is replicated by the switch into every
         # rank's buffer, so the producing SM sends each row once instead of `world` times (8 GPUs: 12.86 ms per step
         # against 13.06 with unicast peer stores and 13.19 with NCCL). Used whenever the fabric offers a multicast
-        # address (multicast=False or VF_GATHER_MC=0 forces the unicast stores).
-        import os
-
+        # address (multicast=False forces the unicast peer stores).
         mc = int(getattr(self.hdl, "multicast_ptr", 0) or 0)
-        want = multicast if multicast is not None else os.environ.get("VF_GATHER_MC", "1") != "0"
+        want = True if multicast is None else bool(multicast)
         self.multicast_ptr = mc if (want and mc != 0) else 0
         self._slot = -1
+
+    def set_next_slot(self, slot: int) -> None:
+        """Pin the slot the next forward writes (a CUDA graph freezes it at capture: give every graph its own)."""
+        self._slot = (slot - 1) % self.slots
 
     def next_slot(self) -> int:
         self._slot = (self._slot + 1) % self.slots

@@ -23,14 +23,27 @@ from .qwen3_5_vision_model import _Packed, _forward_only_guard
 
 
 class ZeroCenteredRMSNorm(nn.Module):
-    """Parameter container of the reference's zero-centred RMSNorm (qwen3_next_attention.py:20-46): ``scale`` starts
-    at zero and the forward multiplies by ``1 + scale``. Used fused (inside vf_mrope_apply); ``forward`` is provided
-    for completeness through the same kernel with an identity rotation disabled."""
+    """The reference's zero-centred RMSNorm (qwen3_next_attention.py:20-46): ``scale`` starts at zero and the forward
+    multiplies by ``1 + scale``, all in fp32, then casts back. Inside MRoPEGatedAttention it runs fused with MRoPE-I
+    (vf_mrope_apply_strided); ``forward`` is the stand-alone vf_rmsnorm_zc kernel."""
 
     def __init__(self, emb_dim, eps=1e-6, dtype=None):
         super().__init__()
         self.scale = nn.Parameter(torch.zeros(emb_dim, dtype=dtype))
         self.eps = eps
+        self._packed = _Packed()
+
+    def one_plus_scale(self):
+        # (1.0 + scale) is evaluated in the parameter's dtype, as the reference does, before the fp32 multiply
+        return self._packed.get("w", [self.scale], lambda: (1.0 + self.scale.detach()).float().contiguous())
+
+    def forward(self, x):
+        _forward_only_guard(self)
+        if not x.is_cuda:
+            raise VFuseError("ZeroCenteredRMSNorm (llm_quest_b200) runs on CUDA sm_100a only; got a CPU tensor")
+        if x.dtype not in (torch.float32, torch.bfloat16):
+            return _lib.rmsnorm_zc(x.float(), self.one_plus_scale(), self.eps).to(x.dtype)
+        return _lib.rmsnorm_zc(x, self.one_plus_scale(), self.eps)
 
 
 class MRoPEGatedAttention(nn.Module):
@@ -60,9 +73,7 @@ class MRoPEGatedAttention(nn.Module):
         ws = [self.w_queries_gate.weight, self.w_keys.weight, self.w_values.weight]
         w_in = c.get("w_in", ws, lambda: torch.cat([w.detach().to(torch.bfloat16) for w in ws], dim=0).contiguous())
         w_out = c.get("w_out", [self.out_proj.weight], lambda: self.out_proj.weight.detach().to(torch.bfloat16).contiguous())
-        qn = c.get("qn", [self.q_norm.scale], lambda: (1.0 + self.q_norm.scale.detach().float()).contiguous())
-        kn = c.get("kn", [self.k_norm.scale], lambda: (1.0 + self.k_norm.scale.detach().float()).contiguous())
-        return w_in, w_out, qn, kn
+        return w_in, w_out, self.q_norm.one_plus_scale(), self.k_norm.one_plus_scale()
 
     def forward(self, x, mask=None, cos=None, sin=None, position_ids=None, attn_mask=None, cache=None):
         """x [b, seq, d_in]; cos/sin [ctx, rot] fp32 tables (GlobalBuffers.get_rope_params); position_ids [3, b, seq]

@@ -10,11 +10,12 @@ the whole tower, the residual stream is fp32, GEMM/attention operands are bf16 a
 hand-written kernel (csrc/):
 
     pixels -> [vf_patch_embed: 5-D TMA gather GEMM + bias + pos-embed]            -> x   fp32
-    per block:  x -> [vf_layernorm] -> h bf16 -> [vf_gemm QKV + bias + axial RoPE] -> qkv bf16
+    block 0:    x -> [vf_layernorm (+ row means = first shift)] -> h bf16
+    per block:  h -> [vf_gemm QKV + bias + axial RoPE (+ folded norm1)]            -> qkv bf16
                 qkv -> [vf_attention_fwd]                                          -> a   bf16
-                a -> [vf_gemm proj + bias + residual]                              -> x   fp32
-                x -> [vf_layernorm] -> h -> [vf_gemm lin1 + bias + tanh-GELU]      -> g   bf16
-                g -> [vf_gemm lin2 + bias + residual]                              -> x   fp32
+                a -> [vf_gemm proj + bias + residual (+ bf16 copy, row partial sums)]  -> x fp32, h bf16
+                [vf_ln_row_stats] -> [vf_gemm lin1 + bias + tanh-GELU (+ folded norm2)] -> g bf16
+                g -> [vf_gemm lin2 + bias + residual (+ bf16 copy, row partial sums)]  -> x fp32, h bf16 ; [vf_ln_row_stats]
     merger:     x -> [vf_layernorm + 2x2 merge gather] -> [lin1 + erf-GELU] -> [lin2 + bias] -> out
 
 Forward only (the reference's callers run it under inference_mode/no_grad).
@@ -93,14 +94,6 @@ def _fold_ln(cache: _Packed, key, lin: nn.Linear, norm: nn.LayerNorm):
     return cache.get(key, [lin.weight, lin.bias, norm.weight, norm.bias], build)
 
 
-def ln_fusion_mode() -> int:
-    """How much LayerNorm is folded into the GEMMs of a block (VF_LN_FUSE): 0 = none (stand-alone kernels), 1 = norm1
-    only (lin2 / patch embedding produce, QKV consumes), 2 = norm1 and norm2 (proj produces, lin1 consumes)."""
-    import os
-
-    return int(os.environ.get("VF_LN_FUSE", "2"))
-
-
 def _as_2d_bf16(x: torch.Tensor) -> torch.Tensor:
     return _lib.to_bf16(x.reshape(-1, x.shape[-1]))
 
@@ -131,19 +124,19 @@ class PatchEmbedding3D(nn.Module):
             f"Input time shape {time} is not divisible by temporal_patch_size {self.temporal_patch_size}"
         )
 
-    def embed_into(self, x, pos=None, ln_work=None):
-        """fp32 [B*S, D] = conv(x) + bias (+ pos[token % n]); the fused entry the tower uses.
-        ln_work: callable (rows, D) -> (xb, stat) buffers for the folded-LayerNorm producer outputs, or None."""
+    def embed_into(self, x, pos=None):
+        """fp32 [B*S, D] = conv(x) + bias (+ pos[token % n]); the fused entry the tower uses."""
         self._check(x)
         B, _, T, H, W = x.shape
         P, tp = self.patch_size, self.temporal_patch_size
+        if P != 16:
+            raise VFuseError(f"PatchEmbedding3D (llm_quest_b200): the TMA patch gather is built for 16x16 patches, got {P}")
         S = (T // tp) * (H // P) * (W // P)
         D = self.conv_proj.out_channels
         w = _w_bf16(self._packed, "w", self.conv_proj.weight, (D, -1))
         bias = _f32(self._packed, "b", self.conv_proj.bias)
         out = torch.empty((B * S, D), dtype=torch.float32, device=x.device)
-        _lib.patch_embed(_lib.to_bf16(x), w, bias, pos, out, P, tp, S, 0,
-                         ln_out=ln_work(B * S, D) if ln_work is not None else None)
+        _lib.patch_embed(_lib.to_bf16(x), w, bias, pos, out, P, tp, S, 0)
         return out, B, S
 
     def forward(self, x):
@@ -198,11 +191,11 @@ class Qwen3_5VisionAttention(nn.Module):
 
     def _require_hd64(self):
         if self.head_dim != 64:
-            raise VFuseError(f"the fused attention / RoPE kernels are built for head_dim 64, got {self.head_dim}")
+            raise VFuseError(f"the fused QKV+RoPE epilogue and the tcgen05 attention are built for head_dim 64, got {self.head_dim}")
 
     def attend(self, h2d, B, S, rope, folded=None, ln_in=None):
         """h2d bf16 [B*S, D] -> context bf16 [B*S, D]. rope = (cos_half, sin_half, period).
-        folded/ln_in: norm1 folded into the QKV GEMM — h2d is then the bf16 copy of the un-normalised stream."""
+        folded/ln_in: norm1 folded into the QKV GEMM — h2d is then the bf16 copy of the shifted, un-normalised stream."""
         self._require_hd64()
         wqkv, bqkv, _, _ = self.packed()
         if folded is not None:
@@ -238,61 +231,42 @@ class Qwen3_5VisionTransformerBlock(nn.Module):
         self.ffn = Qwen3_5VisionFFN(cfg)
         self._packed = _Packed()
 
-    def run_(self, x2d, B, S, rope, work, ln1_ready=False, emit_next=False, rows_ready=False, next_eps=None):
+    def run_(self, x2d, B, S, rope, work, ln1_pending=False, emit_next=False):
         """In-place update of the fp32 residual stream x2d [B*S, D]; `work` holds reusable buffers.
 
         With work["stat"] present the LayerNorms are folded into the GEMMs around them (vf_epilogue.ln_*): the GEMM that
-        produces x also writes its bf16 copy to work["h"], per-row partial sums to work["stat"] and — the warp that
-        completes a row group — (mean, rstd) to work["rows"]; the GEMM that consumes LN(x) multiplies the bf16 copy by
-        the gamma-scaled weight and normalises in its epilogue. ln1_ready: the previous producer (patch embedding or
-        the previous block's lin2) already left h/stat for norm1; rows_ready: it also left work["rows"] (the patch
-        embedding does not: vf_ln_row_stats finishes its partial sums); emit_next: this block's lin2 leaves them for the
-        next block, whose norm1 uses next_eps."""
+        produces x also writes bf16(x - shift) to work["h"] and per-row partial sums of the shifted row to work["stat"];
+        vf_ln_row_stats turns them into (mean', rstd) in work["rows"] and advances work["shift"] to the row's mean; the
+        GEMM that consumes LN(x) multiplies the bf16 copy by the gamma-scaled weight and normalises in its epilogue.
+        ln1_pending: the previous block's lin2 left h/stat for this block's norm1; emit_next: this block's lin2 leaves
+        them for the next block. The first LayerNorm of a chain is a stand-alone kernel on the fp32 stream (it also
+        yields the first shift), so a row's mean never meets the bf16 rounding."""
         c = self._packed
         _, _, wo, bo = self.att.packed()
         w1, b1, w2, b2 = self.ffn.packed()
-        h, g, stat, rows, cnt, flags = (work["h"], work["g"], work.get("stat"), work.get("rows"), work.get("cnt"),
-                                        work.get("flags"))
+        h, g, stat, rows, shift = work["h"], work["g"], work.get("stat"), work.get("rows"), work.get("shift")
         D = x2d.shape[1]
-        inl = cnt is not None            # producer finishes (mean, rstd) itself (VF_LN_INLAUNCH=1)
-        pub = flags is not None          # consumer finishes them itself: publish / poll through `flags` (default)
-        if stat is not None and ln1_ready:
+        fold = stat is not None
+        if fold and ln1_pending:
             wq, bq, csq = _fold_ln(c, "fold_qkv", self.att.qkv, self.norm1)
-            if pub:
-                ln_in = (rows, csq, stat, flags, self.norm1.eps)
-            else:
-                if not rows_ready:
-                    _lib.ln_row_stats(stat, D, self.norm1.eps, rows)
-                ln_in = (rows, csq)
-            ctx = self.att.attend(h, B, S, rope, folded=(wq, bq), ln_in=ln_in)
+            _lib.ln_row_stats(stat, D, self.norm1.eps, rows, shift)
+            ctx = self.att.attend(h, B, S, rope, folded=(wq, bq), ln_in=(rows, csq))
         else:
             n1w, n1b = _f32(c, "n1w", self.norm1.weight), _f32(c, "n1b", self.norm1.bias)
-            _lib.layernorm(x2d, n1w, n1b, h, self.norm1.eps)
+            _lib.layernorm(x2d, n1w, n1b, h, self.norm1.eps, mean_out=shift if fold else None)
             ctx = self.att.attend(h, B, S, rope)
-
-        def producer_args(eps):
-            if pub:
-                return (h, stat, flags)
-            return (h, stat, rows, cnt, eps) if inl else (h, stat)
-
-        nxt = producer_args(self.norm1.eps if next_eps is None else next_eps) if emit_next else None
-        if stat is not None and work.get("fold_norm2"):
+        producer = (h, stat, shift) if fold else None
+        if fold and work.get("fold_norm2"):
             w1f, b1f, cs1 = _fold_ln(c, "fold_lin1", self.ffn.lin1, self.norm2)
-            _lib.gemm(ctx, wo, VF_EPI_BIAS_RES_F32, x2d, bias=bo, res=x2d, ln_out=producer_args(self.norm2.eps))
-            if pub:
-                ln_in = (rows, cs1, stat, flags, self.norm2.eps)
-            else:
-                if not inl:
-                    _lib.ln_row_stats(stat, D, self.norm2.eps, rows)
-                ln_in = (rows, cs1)
-            _lib.gemm(h, w1f, VF_EPI_GELU_TANH_BF16, g, bias=b1f, ln_in=ln_in)
-            _lib.gemm(g, w2, VF_EPI_BIAS_RES_F32, x2d, bias=b2, res=x2d, ln_out=nxt)
-            return
-        n2w, n2b = _f32(c, "n2w", self.norm2.weight), _f32(c, "n2b", self.norm2.bias)
-        _lib.gemm(ctx, wo, VF_EPI_BIAS_RES_F32, x2d, bias=bo, res=x2d)
-        _lib.layernorm(x2d, n2w, n2b, h, self.norm2.eps)
-        _lib.gemm(h, w1, VF_EPI_GELU_TANH_BF16, g, bias=b1)
-        _lib.gemm(g, w2, VF_EPI_BIAS_RES_F32, x2d, bias=b2, res=x2d, ln_out=nxt)
+            _lib.gemm(ctx, wo, VF_EPI_BIAS_RES_F32, x2d, bias=bo, res=x2d, ln_out=producer)
+            _lib.ln_row_stats(stat, D, self.norm2.eps, rows, shift)
+            _lib.gemm(h, w1f, VF_EPI_GELU_TANH_BF16, g, bias=b1f, ln_in=(rows, cs1))
+        else:
+            n2w, n2b = _f32(c, "n2w", self.norm2.weight), _f32(c, "n2b", self.norm2.bias)
+            _lib.gemm(ctx, wo, VF_EPI_BIAS_RES_F32, x2d, bias=bo, res=x2d)
+            _lib.layernorm(x2d, n2w, n2b, h, self.norm2.eps, mean_out=shift if fold else None)
+            _lib.gemm(h, w1, VF_EPI_GELU_TANH_BF16, g, bias=b1)
+        _lib.gemm(g, w2, VF_EPI_BIAS_RES_F32, x2d, bias=b2, res=x2d, ln_out=producer if emit_next else None)
 
     def forward(self, x, cos, sin):
         _forward_only_guard(self)
@@ -325,7 +299,7 @@ class ViTMergeAdapter(nn.Module):
         self.lin2 = nn.Linear(self.merged_size, llm_d_in)
         self._packed = _Packed()
 
-    def merge_project(self, x2d, out=None, dst_rows=None, peer_ptrs=None):
+    def merge_project(self, x2d, out=None, dst_rows=None, peer_ptrs=None, peer_multicast=False):
         """x2d fp32/bf16 [B*S, D] -> [B*S/m^2, llm_d_in]. With `dst_rows` (int32 per merged row) the
         last GEMM scatters bf16 rows straight into `out` (the fused text sequence); with `peer_ptrs` it stores
         them into the gathered buffer of every rank (fused all-gather, see parallel.FusedAllGather)."""
@@ -346,7 +320,7 @@ class ViTMergeAdapter(nn.Module):
         if out is None:
             out = torch.empty((rows // mm, w2.shape[0]), dtype=torch.float32, device=x2d.device)
         mode = VF_EPI_BIAS_F32 if out.dtype == torch.float32 else VF_EPI_BIAS_BF16
-        _lib.gemm(g, w2, mode, out, bias=b2, peer_ptrs=peer_ptrs)
+        _lib.gemm(g, w2, mode, out, bias=b2, peer_ptrs=peer_ptrs, peer_multicast=peer_multicast)
         return out
 
     def forward(self, x):
@@ -412,50 +386,29 @@ class Qwen3_5VisionModel(nn.Module):
 
         return self._packed.get(("rope", str(device)), [self.cos, self.sin], build)
 
+    # How much LayerNorm is folded into the GEMMs of a block: 2 = norm1 and norm2 (default), 1 = norm1 only, 0 = none
+    # (stand-alone vf_layernorm launches). Plain attribute: set it on an instance (tests, A/B measurements).
+    ln_fold = 2
+
     def encode_hidden(self, x):
         """pixels [B,C,T,H,W] -> (fp32 residual stream [B*S, D] after the last block, B, S)."""
         if not x.is_cuda:
             raise VFuseError("Qwen3_5VisionModel (llm_quest_b200) runs on CUDA sm_100a only; got a CPU tensor")
         pos = _f32(self._packed, "pos", self.pos_embed.weight)
-        work = {}
-        mode = ln_fusion_mode()
-        fuse = mode > 0 and len(self.blocks) > 0 and self.pos_embed.embedding_dim % 32 == 0
-        work["fold_norm2"] = mode > 1
-
-        import os
-
-        # who turns the producer's partial sums into (mean, rstd), VF_LN_STATS = "kernel" (a vf_ln_row_stats launch),
-        # "consumer" (the consuming GEMM's epilogue warps do it grid-wide before their first tile, hidden behind the first
-        # main loop; a counter the producer cleared tells when all are done) or "producer" (the producing GEMM's
-        # last-arriving warp per row group: fence + 24 dependent loads cost the epilogue-bound proj GEMM +0.44 ms per step)
-        who = os.environ.get("VF_LN_STATS", "producer" if os.environ.get("VF_LN_INLAUNCH") == "1" else "kernel")
-
-        def ln_work(rows, D):
-            work["h"] = torch.empty((rows, D), dtype=torch.bfloat16, device=x.device)
-            work["stat"] = torch.empty((D // 32, rows, 2), dtype=torch.float32, device=x.device)
-            work["rows"] = torch.empty((rows, 2), dtype=torch.float32, device=x.device)
-            groups = (rows + 31) // 32
-            if who == "producer":   # contribution counters (zero before and after every launch: allocated once)
-                work["cnt"] = self._packed.get(("ln_cnt", rows, str(x.device)), [],
-                                               lambda: torch.zeros((groups,), dtype=torch.int32, device=x.device))
-            if who == "consumer":   # the consumer's "statistics done" counter (cleared by every producer launch)
-                work["flags"] = self._packed.get(("ln_flags", str(x.device)), [],
-                                                 lambda: torch.zeros((1,), dtype=torch.int32, device=x.device))
-            return (work["h"], work["stat"], work["flags"]) if who == "consumer" else (work["h"], work["stat"])
-
-        x2d, B, S = self.patch_embed.embed_into(x, pos, ln_work if fuse else None)
+        x2d, B, S = self.patch_embed.embed_into(x, pos)
         cos_h, sin_h = self._rope_half(x.device)
         rope = (cos_h, sin_h, self.n_spatial_patches)
-        D = x2d.shape[1]
-        if not fuse:
-            work["h"] = torch.empty((B * S, D), dtype=torch.bfloat16, device=x.device)
+        rows, D = x2d.shape
+        work = {"h": torch.empty((rows, D), dtype=torch.bfloat16, device=x.device), "fold_norm2": self.ln_fold > 1}
+        if self.ln_fold > 0 and len(self.blocks) > 0 and D % 32 == 0:
+            work["stat"] = torch.empty((D // 32, rows, 2), dtype=torch.float32, device=x.device)
+            work["rows"] = torch.empty((rows, 2), dtype=torch.float32, device=x.device)
+            work["shift"] = torch.empty((rows,), dtype=torch.float32, device=x.device)
         if len(self.blocks):
-            work["g"] = torch.empty((B * S, self.blocks[0].ffn.lin1.out_features), dtype=torch.bfloat16, device=x.device)
+            work["g"] = torch.empty((rows, self.blocks[0].ffn.lin1.out_features), dtype=torch.bfloat16, device=x.device)
         last = len(self.blocks) - 1
         for i, block in enumerate(self.blocks):
-            block.run_(x2d, B, S, rope, work, ln1_ready=fuse, emit_next=fuse and i < last,
-                       rows_ready=fuse and i > 0 and work.get("cnt") is not None,
-                       next_eps=self.blocks[i + 1].norm1.eps if i < last else None)
+            block.run_(x2d, B, S, rope, work, ln1_pending=i > 0, emit_next=i < last)
         return x2d, B, S
 
     def forward(self, x, out=None, dst_rows=None, gather=None):
@@ -470,7 +423,8 @@ class Qwen3_5VisionModel(nn.Module):
         x2d, B, S = self.encode_hidden(x)
         if gather is not None:
             slot = gather.next_slot()
-            self.merge_adapter.merge_project(x2d, out=gather.local_rows(slot), peer_ptrs=gather.peer_ptrs(slot))
+            self.merge_adapter.merge_project(x2d, out=gather.local_rows(slot), peer_ptrs=gather.peer_ptrs(slot),
+                                             peer_multicast=bool(gather.multicast_ptr))
             gather.barrier()
             return gather.gathered(slot).view(gather.world * B, -1, gather.cols)
         if dst_rows is not None:

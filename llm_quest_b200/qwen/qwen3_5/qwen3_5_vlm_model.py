@@ -60,7 +60,7 @@ class Qwen3_5VLM(nn.Module):
         # every new token (qwen3_5_generate_multimodal.py:107-123); with the cache on, the tower runs once per
         # pixel tensor and later calls only redo the (cheap) gather/scatter + position ids
         self._vision_cache_on = False
-        self._vision_cache = None   # (signature, merged rows bf16 [n_vis, D])
+        self._vision_cache = None   # dict: tower parameter versions, image identity, merged rows bf16 [n_vis, D]
 
     # -- reference API ----------------------------------------------------------------------------
     def get_feeds_3d_shape(self, image_pixels):
@@ -87,9 +87,15 @@ class Qwen3_5VLM(nn.Module):
 
     # -- vision-feature cache ------------------------------------------------------------------------
     def enable_vision_cache(self, on: bool = True):
-        """Keep the merged vision embeddings of the last ``image_pixels`` tensor and reuse them while the
-        same tensor (storage, shape, version) is passed again and the tower's weights are unchanged.
-        Off by default: the reference recomputes every call."""
+        """Keep the merged vision embeddings of the last ``image_pixels`` tensor and reuse them while the SAME tensor
+        object is passed again (or the same explicit ``image_id``) and the tower's weights are unchanged.
+        Off by default: the reference recomputes every call.
+
+        The key is object identity, not storage identity: the cache holds a reference to the pixel tensor, so its
+        memory cannot be freed and handed to the next image by the caching allocator (a (data_ptr, shape) key would
+        then silently serve the previous image's embeddings). Content changed IN PLACE through torch ops bumps
+        ``_version`` and invalidates the entry; writes made by raw-pointer kernels (libvfuse's own, e.g.
+        vf_preprocess_u8 into a caller-owned buffer) do not — pass a fresh ``image_id`` or call clear_vision_cache()."""
         self._vision_cache_on = bool(on)
         if not on:
             self._vision_cache = None
@@ -98,32 +104,33 @@ class Qwen3_5VLM(nn.Module):
     def clear_vision_cache(self):
         self._vision_cache = None
 
-    def _vision_signature(self, image_pixels):
+    def _cached_vision_rows(self, image_pixels, n_vis, D, image_id=None):
         ver = lambda t: 0 if t.is_inference() else t._version
-        sig = [(image_pixels.data_ptr(), tuple(image_pixels.shape), image_pixels.dtype, ver(image_pixels))]
-        for prm in self.vision_model.parameters():
-            sig.append((prm.data_ptr(), ver(prm)))
-        return tuple(sig)
-
-    def _cached_vision_rows(self, image_pixels, n_vis, D):
-        sig = self._vision_signature(image_pixels)
+        params = tuple((prm.data_ptr(), ver(prm)) for prm in self.vision_model.parameters())
         hit = self._vision_cache
-        if hit is not None and hit[0] == sig:
-            return hit[1]
+        if hit is not None and hit["params"] == params and hit["rows"].shape == (n_vis, D):
+            if image_id is not None:
+                same = hit["image_id"] == image_id
+            else:
+                same = hit["image_id"] is None and hit["pixels"] is image_pixels and hit["version"] == ver(image_pixels)
+            if same:
+                return hit["rows"]
         rows = torch.empty((n_vis, D), dtype=torch.bfloat16, device=image_pixels.device)
         vm = self.vision_model
         x2d, _, _ = vm.encode_hidden(image_pixels)
         vm.merge_adapter.merge_project(x2d, out=rows)
-        self._vision_cache = (sig, rows)
+        self._vision_cache = {"params": params, "image_id": image_id, "pixels": image_pixels, "version": ver(image_pixels),
+                              "rows": rows}
         return rows
 
     # -- the fused path ---------------------------------------------------------------------------
-    def encode_and_fuse(self, input_ids, image_pixels=None, feeds_3d_shape=None, check=True):
+    def encode_and_fuse(self, input_ids, image_pixels=None, feeds_3d_shape=None, check=True, image_id=None):
         """Everything of ``forward`` before the text model: returns (inputs_embs bf16 [b, seq, D],
         position_ids int64 [3, b, seq], image_mask bool [b, seq] or None).
 
         check=True validates, like masked_scatter does, that the vision tower produced at least as
         many rows as there are placeholders (one 4-byte device->host read); check=False skips it.
+        image_id (any hashable, optional): explicit identity of the image for the vision-feature cache.
         """
         table = self.language_model.emb_dict.weight
         if not input_ids.is_cuda:
@@ -150,7 +157,7 @@ class Qwen3_5VLM(nn.Module):
                     )
             if self._vision_cache_on:
                 # one kernel moves text rows from the table and vision rows from the cached embeddings
-                rows = self._cached_vision_rows(image_pixels, n_vis, D)
+                rows = self._cached_vision_rows(image_pixels, n_vis, D, image_id)
                 _lib.embed_gather_scatter(input_ids, table.detach(), rows, row_map, inputs_embs)
             else:
                 # text rows: gathered from the table; placeholder rows are written by the merger GEMM epilogue

@@ -193,8 +193,9 @@ def make_fusion():
         ids[rng.random(size=(b, seq)) < 0.3] = TOK
         ids_t = torch.tensor(ids, dtype=torch.long)
         n_true = int((ids == TOK).sum())
-        table = torch.randn(64, D).to(torch.bfloat16)
-        vis = torch.randn(n_true + 3, D)
+        tg = torch.Generator().manual_seed(1000 + seq)      # seeded: the fixture reproduces byte for byte
+        table = torch.randn(64, D, generator=tg).to(torch.bfloat16)
+        vis = torch.randn(n_true + 3, D, generator=tg)
         embs = table[ids_t]
         mask = ids_t == TOK
         ref = embs.masked_scatter(mask.unsqueeze(-1).expand_as(embs), vis.to(embs.dtype))
@@ -299,13 +300,73 @@ def make_text_attention():
                GOLD / "text_attention.pt")
 
 
+def make_part2_and_tiny():
+    """Round-2 surface: Part-2 get_embeddings + concat (multimodal/vlm_engine.py:5-20,114), TINY_VIT_CONFIG dims
+    (config.py:175-186: 4x4 patches, head_dim 32; 2 of the 12 layers to keep the fixture small), stand-alone GELU
+    (vit_transformer_block.py:43-44) and ZeroCenteredRMSNorm.forward (qwen3_next_attention.py:41-46)."""
+    import config
+    from llm_quest.multimodal.vision_transformer.vit_model import ViTModel
+    from llm_quest.multimodal.vision_transformer.vit_transformer_block import GELU
+    from llm_quest.multimodal.vlm_engine import get_embeddings
+    from llm_quest.qwen.qwen3_next.qwen3_next_attention import ZeroCenteredRMSNorm
+
+    g = torch.Generator().manual_seed(2024)
+
+    class GPT(torch.nn.Module):      # the two tables get_embeddings reads (gpt/gpt_model.py: emb_dict, pos_emb_dict)
+        def __init__(self):
+            super().__init__()
+            self.emb_dict = torch.nn.Embedding(500, 64)
+            self.pos_emb_dict = torch.nn.Embedding(32, 64)
+
+    torch.manual_seed(123)
+    gpt = GPT().eval()
+    ids = torch.randint(0, 500, (3, 20), generator=g)
+    vis = torch.randn(3, 5, 64, generator=g)
+    with torch.no_grad():
+        text = get_embeddings(ids, gpt)
+        fused = torch.cat([vis, text], dim=1)                                   # vlm_engine.py:114
+    assert torch.equal(VO.get_embeddings(ids, gpt.emb_dict.weight, gpt.pos_emb_dict.weight), text)
+
+    cfg = dict(config.TINY_VIT_CONFIG, n_layers=2)
+    torch.manual_seed(123)
+    vit = ViTModel(cfg).eval()
+    round_module_(vit)
+    img = bf16_exact(torch.randn(4, 3, 32, 32, generator=g))
+    with torch.no_grad():
+        hid, logits = vit(img, output_hidden_states=True), vit(img)
+    sd = {k: v.detach().clone() for k, v in vit.state_dict().items()}
+    e_h = VO.max_norm_err(VO.vit_forward(sd, cfg, img, output_hidden_states=True), hid)
+    e_l = VO.max_norm_err(VO.vit_forward(sd, cfg, img), logits)
+    assert e_h <= 2e-5 and e_l <= 2e-5, (e_h, e_l)
+    print(f"TINY_VIT_CONFIG dims (2 layers): oracle vs reference hidden {e_h:.2e} logits {e_l:.2e}")
+
+    x = torch.randn(6, 50, generator=g) * 3
+    with torch.no_grad():
+        y_gelu = GELU()(x)
+    assert torch.equal(VO.gelu_erf(x), y_gelu)
+    norm = ZeroCenteredRMSNorm(64)
+    with torch.no_grad():
+        norm.scale.add_(0.2 * torch.randn(64, generator=g))
+        xn = torch.randn(5, 7, 64, generator=g) * 2 + 0.3
+        y_norm = norm(xn)
+        y_norm_bf16 = norm(xn.to(torch.bfloat16))
+    assert torch.equal(VO.zero_centered_rmsnorm(xn, norm.scale.detach()), y_norm)
+    print("get_embeddings / GELU / ZeroCenteredRMSNorm: oracle == reference (bit-exact)")
+    torch.save({"part2": {"ids": ids, "tok": gpt.emb_dict.weight.detach().clone(), "pos": gpt.pos_emb_dict.weight.detach().clone(),
+                          "vision": vis, "text": text, "fused": fused},
+                "tiny_vit": {"cfg": cfg, "state_dict": {k: v.to(torch.bfloat16) for k, v in sd.items()}, "images": img.to(torch.bfloat16),
+                             "hidden": hid.clone(), "logits": logits.clone()},
+                "gelu": {"x": x, "y": y_gelu}, "rmsnorm": {"x": xn, "scale": norm.scale.detach().clone(), "y": y_norm, "y_bf16": y_norm_bf16}},
+               GOLD / "part2_tiny.pt")
+
+
+MAKERS = {"fusion": lambda: make_fusion(), "rope": lambda: make_rope_and_merge(), "qwen": lambda: make_qwen_tower(),
+          "vit": lambda: make_vit(), "text_attention": lambda: make_text_attention(), "part2_tiny": lambda: make_part2_and_tiny()}
+
 if __name__ == "__main__":
     GOLD.mkdir(parents=True, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
-    make_fusion()
-    make_rope_and_merge()
-    make_qwen_tower()
-    make_vit()
-    make_text_attention()
+    for name in (sys.argv[1:] or list(MAKERS)):      # no argument: every fixture
+        MAKERS[name]()
     for f in sorted(GOLD.glob("*.pt")):
         print(f"{f.name}: {f.stat().st_size / 1024:.0f} KiB")

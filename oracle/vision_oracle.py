@@ -241,6 +241,12 @@ def vit_forward(sd: dict, cfg: dict, images: torch.Tensor, output_hidden_states:
     return x[:, 0] @ sd["classifier.weight"].t() + sd["classifier.bias"]
 
 
+def get_embeddings(text_input: torch.Tensor, tok_table: torch.Tensor, pos_table: torch.Tensor):
+    """llm_quest/multimodal/vlm_engine.py:5-20 — emb_dict(ids) + pos_emb_dict(arange(seq)); the Part-2 fusion then
+    concatenates [vision ‖ text] along dim 1 (vlm_engine.py:114, vlm_generation.py:66)."""
+    return tok_table[text_input] + pos_table[torch.arange(text_input.shape[1])]
+
+
 def vit_adapter_forward(sd: dict, x: torch.Tensor):
     """ViTAdapter.forward (vit_engine.py:44-59): 'simple' = one Linear, 'ffn' = Linear-GELU(erf)-Linear."""
     if "adapter.weight" in sd:

@@ -52,3 +52,8 @@ def golden_vit():
 @pytest.fixture(scope="session")
 def golden_text_attention():
     return torch.load(GOLDEN / "text_attention.pt", map_location="cpu", weights_only=True)
+
+
+@pytest.fixture(scope="session")
+def golden_part2():
+    return load_golden("part2_tiny.pt")

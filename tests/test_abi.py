@@ -35,7 +35,7 @@ def test_header_symbols_exported(lib):
 def test_version_and_error_string(lib):
     lib.vf_version.restype = ctypes.c_int
     lib.vf_last_error.restype = ctypes.c_char_p
-    assert lib.vf_version() == 100
+    assert lib.vf_version() == 200
     assert isinstance(lib.vf_last_error(), bytes)
 
 
@@ -190,7 +190,7 @@ def test_hf_vision_weight_remap_round_trip():
 def test_fold_layernorm_host_side_identity():
     """_fold_ln (host side of the folded LayerNorm): rstd * (x W'^T - mean * colsum) + b' == LN(x) W^T + b in fp32 up to
     the bf16 rounding of W' — and colsum is the sum of the ROUNDED weight, the one the tensor cores multiply by."""
-    from llm_quest_b200.qwen.qwen3_5.qwen3_5_vision_model import _Packed, _fold_ln, ln_fusion_mode
+    from llm_quest_b200.qwen.qwen3_5.qwen3_5_vision_model import Qwen3_5VisionModel, _Packed, _fold_ln
 
     torch.manual_seed(3)
     d, n = 96, 40
@@ -212,4 +212,9 @@ def test_fold_layernorm_host_side_identity():
     with torch.no_grad():
         norm.weight.mul_(1.5)                                       # in-place edit bumps _version: cache must rebuild
     assert _fold_ln(cache, "k", lin, norm)[0] is not wf
-    assert ln_fusion_mode() in (0, 1, 2)
+    assert Qwen3_5VisionModel.ln_fold == 2          # both LayerNorms of a block folded by default
+    # the identity holds for any row shift s: x' = x - s, mean' = mean(x')
+    xs = x - 5.0
+    with torch.no_grad():
+        shifted = rstd * (xs @ wf.float().t() - xs.mean(1, keepdim=True) * cs[None]) + bf_[None]
+    assert (shifted - ref).abs().max() / ref.abs().max() < 5e-3

@@ -138,19 +138,23 @@ def _fold(w, b, gamma, beta):
 
 
 @pytest.mark.parametrize("M", [777, 1024])
-def test_gemm_folded_layernorm_producer(L, M):
-    """bias_res_f32 with ln_out: bf16 copy of the rows + per-32-column partial (sum, sum of squares)."""
+@pytest.mark.parametrize("with_shift", [False, True])
+def test_gemm_folded_layernorm_producer(L, M, with_shift):
+    """bias_res_f32 with ln_out: bf16 copy of the rows minus their shift + per-32-column partial (sum, sum of squares)
+    of the shifted rows; the fp32 rows themselves are not shifted."""
     N, K = 768, 256
     a, w, b = bf(rnd(M, K, seed=60)), bf(rnd(N, K, seed=61, scale=0.05)), rnd(N, seed=62)
     res = rnd(M, N, seed=63) + 0.3
+    shift = (rnd(M, seed=64) * 3.0) if with_shift else torch.zeros(M)
     x = dev(res.clone())
     xb = torch.zeros((M, N), dtype=torch.bfloat16, device="cuda")
     stat = torch.full((N // 32, M, 2), float("nan"), device="cuda")
-    L.gemm(dev(a), dev(w), L.VF_EPI_BIAS_RES_F32, x, bias=dev(b), res=x, ln_out=(xb, stat))
+    L.gemm(dev(a), dev(w), L.VF_EPI_BIAS_RES_F32, x, bias=dev(b), res=x, ln_out=(xb, stat, dev(shift) if with_shift else None))
     ref = a.float() @ w.float().t() + b + res
     check_close(x, ref, tol=2e-3, what="producer fp32 rows")
-    assert torch.equal(xb.cpu(), bf(x.cpu())), "bf16 copy is not the rounding of the fp32 row"
-    blocks = x.cpu().view(M, N // 32, 32)
+    xs = x.cpu() - shift[:, None]
+    assert torch.equal(xb.cpu(), bf(xs)), "bf16 copy is not the rounding of the shifted fp32 row"
+    blocks = xs.view(M, N // 32, 32)
     torch.testing.assert_close(stat[:, :, 0].cpu().t(), blocks.sum(-1), rtol=1e-5, atol=1e-4)
     torch.testing.assert_close(stat[:, :, 1].cpu().t(), (blocks * blocks).sum(-1), rtol=1e-5, atol=1e-4)
 
@@ -160,10 +164,11 @@ def test_gemm_folded_layernorm_producer(L, M):
 def test_gemm_residual_tma_epilogue_matches_staged_epilogue_bit_exact(L, with_ln, N):
     """Large M takes the CTA-pair kernel whose residual epilogue runs through TMA (32x32 blocks updated in place in
     shared memory); small M takes the single-CTA kernel with the staged register epilogue. Same rows, same bits —
-    fp32 rows, bf16 copy and LayerNorm partial sums — and a ragged last row block (4500 = 35 * 128 + 20)."""
+    fp32 rows, shifted bf16 copy and LayerNorm partial sums — and a ragged last row block (4500 = 35 * 128 + 20)."""
     M, K = 4500, 320          # N = 800: the last 256-wide column tile is ragged (blocks right of N are skipped / clipped)
     a, w, b = dev(bf(rnd(M, K, seed=90))), dev(bf(rnd(N, K, seed=91, scale=0.05))), dev(rnd(N, seed=92))
     res = rnd(M, N, seed=93) + 0.25
+    shift = dev(rnd(M, seed=94) * 0.5 + 0.25)
     ref = a.float().cpu() @ w.float().cpu().t() + b.cpu() + res
 
     def run(rows):
@@ -171,15 +176,8 @@ def test_gemm_residual_tma_epilogue_matches_staged_epilogue_bit_exact(L, with_ln
         n = x.shape[0]
         xb = torch.zeros((n, N), dtype=torch.bfloat16, device="cuda")
         stat = torch.full((N // 32, n, 2), float("nan"), device="cuda")
-        mr = torch.full((n, 2), float("nan"), device="cuda")
-        cnt = torch.zeros(((n + 31) // 32,), dtype=torch.int32, device="cuda")
-        inl = N % 128 == 0      # in-launch (mean, rstd) need whole column ranges per epilogue warp
-        for _ in range(2):      # twice: the launch has to leave its contribution counters at zero
-            x.copy_(res[rows])
-            ln = ((xb, stat, mr, cnt, 1e-6) if inl else (xb, stat)) if with_ln else None
-            L.gemm(a[rows], w, L.VF_EPI_BIAS_RES_F32, x, bias=b, res=x, ln_out=ln)
-        assert int(cnt.abs().sum()) == 0
-        return x.cpu(), xb.cpu(), stat.cpu(), mr.cpu() if inl else None
+        L.gemm(a[rows], w, L.VF_EPI_BIAS_RES_F32, x, bias=b, res=x, ln_out=(xb, stat, shift[rows].contiguous()) if with_ln else None)
+        return x.cpu(), xb.cpu(), stat.cpu()
 
     big = run(slice(0, M))
     check_close(big[0], ref, tol=2e-3, what="TMA residual epilogue vs fp32 oracle")
@@ -190,15 +188,10 @@ def test_gemm_residual_tma_epilogue_matches_staged_epilogue_bit_exact(L, with_ln
         if with_ln:
             assert torch.equal(big[1][lo:hi], small[1]), "bf16 copies differ"
             assert torch.equal(big[2][:, lo:hi], small[2]), "LayerNorm partial sums differ"
-            if big[3] is not None:
-                assert torch.equal(big[3][lo:hi], small[3]), "in-launch (mean, rstd) differ"
     if with_ln:
-        assert torch.equal(big[1], bf(big[0]))
-        blocks = big[0].view(M, N // 32, 32)
-        torch.testing.assert_close(big[2][:, :, 0].t(), blocks.sum(-1), rtol=1e-5, atol=1e-4)
-        if big[3] is not None:
-            torch.testing.assert_close(big[3][:, 0], big[0].mean(1), rtol=1e-4, atol=1e-5)
-            torch.testing.assert_close(big[3][:, 1], (big[0].var(1, unbiased=False) + 1e-6).rsqrt(), rtol=1e-4, atol=1e-5)
+        xs = big[0] - shift.cpu()[:, None]
+        assert torch.equal(big[1], bf(xs))
+        torch.testing.assert_close(big[2][:, :, 0].t(), xs.view(M, N // 32, 32).sum(-1), rtol=1e-5, atol=1e-4)
 
 
 @pytest.mark.parametrize("mode", ["tanh", "erf", "qkv"])
@@ -222,6 +215,10 @@ def test_gemm_folded_layernorm_consumer(L, mode):
     L.ln_row_stats(stat, D, 1e-6, rows)
     torch.testing.assert_close(rows[:, 0].cpu(), xr.mean(1), rtol=1e-4, atol=1e-5)
     torch.testing.assert_close(rows[:, 1].cpu(), (xr.var(1, unbiased=False) + 1e-6).rsqrt(), rtol=1e-4, atol=1e-5)
+    # variant 1 = the Part-1 LayerNorm (eps added to the std)
+    rows1 = torch.empty((M, 2), device="cuda")
+    L.ln_row_stats(stat, D, 1e-5, rows1, variant=1)
+    torch.testing.assert_close(rows1[:, 1].cpu(), 1.0 / (xr.var(1, unbiased=False).sqrt() + 1e-5), rtol=1e-4, atol=1e-5)
     lin = torch.nn.functional.layer_norm(xr, (D,), gamma, beta, 1e-6) @ w.t() + b
     out = torch.zeros((M, N), dtype=torch.bfloat16, device="cuda")
     if mode == "qkv":
@@ -240,53 +237,38 @@ def test_gemm_folded_layernorm_consumer(L, mode):
     check_close(out, ref, tol=6e-3, what=f"folded layernorm -> {mode}")
 
 
-@pytest.mark.parametrize("mode,M", [("tanh", 4500), ("qkv", 4704), ("erf", 300)])
-def test_gemm_folded_layernorm_statistics_published_by_the_consumer(L, mode, M):
-    """No launch between producer and consumer: before their first tile the consumer's epilogue warps add up the
-    producer's partial sums grid-wide and count themselves in on a counter the producer cleared. Run twice on the same
-    buffers (the counter must be cleared again), large M (CTA pairs) and small M (single-CTA kernels, staged epilogues)."""
-    nh, nw = 7, 7 * 2
-    n = nh * nw
-    D = 768
-    N = 3 * D if mode == "qkv" else 3072
-    a, w0, b0 = dev(bf(rnd(M, 128, seed=70))), dev(bf(rnd(D, 128, seed=71, scale=0.1))), dev(rnd(D, seed=72))
-    res = rnd(M, D, seed=73) * 2.0 + 0.5
+@pytest.mark.parametrize("offset", [10.0, 50.0])
+def test_gemm_folded_layernorm_rows_with_large_mean(L, offset):
+    """Rows whose mean is 10 / 50 standard deviations away from zero (outlier rows of real checkpoints): with the row
+    shift (here: the exact mean of the residual BEFORE the producing GEMM, as in the tower, where it comes from the
+    previous LayerNorm point) the folded chain stays at the accuracy of LayerNorm-then-GEMM; without it the bf16
+    rounding of x swamps the row's spread, which is why the shift exists."""
+    M, D, N = 2048, 768, 1024
+    a, w0, b0 = bf(rnd(M, 128, seed=70)), bf(rnd(D, 128, seed=71, scale=0.1)), rnd(D, seed=72)
+    res = rnd(M, D, seed=73) + offset * (1.0 + 0.1 * rnd(M, 1, seed=78))          # per-row means around `offset`, sigma 1
     gamma, beta = 1.0 + 0.2 * rnd(D, seed=74), 0.1 * rnd(D, seed=75)
     w, b = rnd(N, D, seed=76, scale=0.05), rnd(N, seed=77)
     wf, bfold, cs = _fold(w, b, gamma, beta)
-    wf, bfold, cs = dev(wf), dev(bfold), dev(cs)
-    xb = torch.empty((M, D), dtype=torch.bfloat16, device="cuda")
-    stat = torch.empty((D // 32, M, 2), device="cuda")
-    flags = torch.full((1,), 12345, dtype=torch.int32, device="cuda")            # stale counter on purpose
-    rows = torch.full((M, 2), float("nan"), device="cuda")
-    out = torch.zeros((M, N), dtype=torch.bfloat16, device="cuda")
-    cos, sin = VO.axial_rope_tables(10_000, 64, nh, nw)
-    rope = (dev(cos[:, :32].contiguous()), dev(sin[:, :32].contiguous()), n, 2 * D)
-    for it in range(2):
-        x = dev((res + it).clone())
-        L.gemm(a, w0, L.VF_EPI_BIAS_RES_F32, x, bias=b0, res=x, ln_out=(xb, stat, flags))
-        assert int(flags[0]) == 0, "the producer has to clear the consumer's counter"
-        if mode == "qkv":
-            L.gemm(xb, wf, L.VF_EPI_QKV_ROPE_BF16, out, bias=bfold, ln_in=(rows, cs, stat, flags, 1e-6), rope=rope)
-        else:
-            epi = L.VF_EPI_GELU_TANH_BF16 if mode == "tanh" else L.VF_EPI_GELU_ERF_BF16
-            L.gemm(xb, wf, epi, out, bias=bfold, ln_in=(rows, cs, stat, flags, 1e-6))
-        torch.cuda.synchronize()
-        assert int(flags[0]) > 0 and int(flags[0]) % 8 == 0, "every epilogue warp of the grid counts itself in once"
+    errs = {}
+    for use_shift in (True, False):
+        x = dev(res.clone())
+        shift = dev(res.mean(1).contiguous()) if use_shift else None
+        xb = torch.empty((M, D), dtype=torch.bfloat16, device="cuda")
+        stat = torch.empty((D // 32, M, 2), device="cuda")
+        L.gemm(dev(a), dev(w0), L.VF_EPI_BIAS_RES_F32, x, bias=dev(b0), res=x, ln_out=(xb, stat, shift))
+        rows = torch.empty((M, 2), device="cuda")
+        L.ln_row_stats(stat, D, 1e-6, rows, shift)
         xr = x.cpu()
-        torch.testing.assert_close(rows[:, 0].cpu(), xr.mean(1), rtol=1e-4, atol=1e-5)
-        torch.testing.assert_close(rows[:, 1].cpu(), (xr.var(1, unbiased=False) + 1e-6).rsqrt(), rtol=1e-4, atol=1e-5)
-        lin = torch.nn.functional.layer_norm(xr, (D,), gamma, beta, 1e-6) @ w.t() + b
-        if mode == "qkv":
-            B_ = M // n
-            H = D // 64
-            qkv = lin.view(B_, n, 3, H, 64)
-            q, k, v = (qkv[:, :, i].transpose(1, 2) for i in range(3))
-            q, k = VO.rotate_half_apply(q, cos, sin), VO.rotate_half_apply(k, cos, sin)
-            ref = torch.stack([t.transpose(1, 2) for t in (q, k, v)], dim=2).reshape(M, N)
-        else:
-            ref = (VO.gelu_tanh if mode == "tanh" else VO.gelu_erf)(lin)
-        check_close(out, ref, tol=6e-3, what=f"consumer-published statistics -> {mode} (run {it})")
+        if use_shift:   # the shift has been advanced to the rows' true means
+            torch.testing.assert_close(shift.cpu(), xr.mean(1), rtol=1e-5, atol=1e-4)
+            torch.testing.assert_close(rows[:, 1].cpu(), (xr.var(1, unbiased=False) + 1e-6).rsqrt(), rtol=1e-3, atol=1e-5)
+        out = torch.zeros((M, N), dtype=torch.bfloat16, device="cuda")
+        L.gemm(xb, dev(wf), L.VF_EPI_GELU_TANH_BF16, out, bias=dev(bfold), ln_in=(rows, dev(cs)))
+        ref = VO.gelu_tanh(torch.nn.functional.layer_norm(xr, (D,), gamma, beta, 1e-6) @ w.t() + b)
+        errs[use_shift] = VO.max_norm_err(out.float().cpu(), ref)
+    print(f"rows with mean {offset} sigma: folded LayerNorm error with shift {errs[True]:.2e}, without {errs[False]:.2e}")
+    assert errs[True] <= 6e-3, errs
+    assert errs[False] > 2 * errs[True], "the shift should matter for such rows"
 
 
 def test_gemm_folded_layernorm_rejects_bad_arguments(L):
@@ -317,27 +299,6 @@ def test_patch_embed3d(L, B, T, H, W, D):
     L.patch_embed(dev(x), dev(w.reshape(D, -1).contiguous()), dev(b), dev(pos), out, P, tp, S, 0)
     ref = VO.patch_embed3d(x.float(), w.float(), b) + pos[:n].repeat(T // tp, 1)[None]
     check_close(out.view(B, S, D), ref, tol=2e-3, what=f"patch_embed3d {B}x{T}x{H}x{W}")
-
-
-def test_patch_embed3d_folded_layernorm_outputs(L):
-    """vf_patch_embed_ln: bf16 copy + partial row sums next to the fp32 rows (ragged tile rectangles included)."""
-    B, T, H, W, D, P, tp = 2, 2, 160, 48, 128, 16, 2
-    x = bf(rnd(B, 3, T, H, W, seed=20))
-    w = bf(rnd(D, 3, tp, P, P, seed=21, scale=0.03))
-    b = rnd(D, seed=22)
-    n = (H // P) * (W // P)
-    pos = rnd(n, D, seed=23)
-    S = (T // tp) * n
-    out = torch.full((B * S, D), float("nan"), device="cuda")
-    xb = torch.zeros((B * S, D), dtype=torch.bfloat16, device="cuda")
-    stat = torch.full((D // 32, B * S, 2), float("nan"), device="cuda")
-    L.patch_embed(dev(x), dev(w.reshape(D, -1).contiguous()), dev(b), dev(pos), out, P, tp, S, 0, ln_out=(xb, stat))
-    ref = VO.patch_embed3d(x.float(), w.float(), b) + pos[:n].repeat(T // tp, 1)[None]
-    check_close(out.view(B, S, D), ref, tol=2e-3, what="patch_embed3d (ln outputs)")
-    assert torch.equal(xb.cpu(), bf(out.cpu()))
-    blocks = out.cpu().view(B * S, D // 32, 32)
-    torch.testing.assert_close(stat[:, :, 0].cpu().t(), blocks.sum(-1), rtol=1e-5, atol=1e-4)
-    torch.testing.assert_close(stat[:, :, 1].cpu().t(), (blocks * blocks).sum(-1), rtol=1e-5, atol=1e-4)
 
 
 def test_patch_embed2d_with_cls_rows(L):
@@ -693,3 +654,68 @@ def test_error_paths_on_device(L):
                                              None, 0, 0, 0, 1, 64, 2, 2, 128, 0.1, 1, None), "vf_attention_gqa_fwd")
     with pytest.raises(L.VFuseError, match="CPU tensor"):
         L.gemm(a.cpu(), w, L.VF_EPI_BIAS_BF16, out)
+
+
+# ------------------------------------------------------------------------------------------------
+# round-2 surface kernels: stand-alone GELU / zero-centred RMSNorm, Part-2 text rows, small patches, head_dim != 64
+# ------------------------------------------------------------------------------------------------
+def test_gelu_and_rmsnorm_goldens(L, golden_part2):
+    g = golden_part2
+    y = L.gelu(dev(g["gelu"]["x"]))
+    torch.testing.assert_close(y.cpu(), g["gelu"]["y"], rtol=2e-6, atol=2e-6)
+    x = rnd(1000, 37, seed=5) * 4                      # odd element count: vector body + scalar tail
+    torch.testing.assert_close(L.gelu(dev(x)).cpu(), VO.gelu_erf(x), rtol=2e-6, atol=2e-6)
+    torch.testing.assert_close(L.gelu(dev(x), tanh_form=True).cpu(), VO.gelu_tanh(x), rtol=2e-6, atol=2e-6)
+    r = g["rmsnorm"]
+    w = (1.0 + r["scale"]).float().contiguous()
+    torch.testing.assert_close(L.rmsnorm_zc(dev(r["x"]), dev(w), 1e-6).cpu(), r["y"], rtol=2e-6, atol=2e-6)
+    got = L.rmsnorm_zc(dev(r["x"].to(torch.bfloat16)), dev(w), 1e-6)
+    assert got.dtype == torch.bfloat16
+    assert (got.float().cpu() - r["y_bf16"].float()).abs().max() <= 2.0 ** -7 * r["y_bf16"].float().abs().max()
+
+
+def test_embed_pos_concat_golden_exact(L, golden_part2):
+    """Part-2 fusion: token + position embeddings written into rows n_vis.. of the fused buffer — exact fp32 adds, the
+    vision rows of the buffer untouched."""
+    p2 = golden_part2["part2"]
+    b, seq = p2["ids"].shape
+    n_vis = p2["vision"].shape[1]
+    fused = torch.zeros((b, n_vis + seq, 64), device="cuda")
+    fused[:, :n_vis] = dev(p2["vision"])
+    L.embed_pos_concat(dev(p2["ids"]), dev(p2["tok"]), dev(p2["pos"]), fused, n_vis)
+    assert torch.equal(fused.cpu(), p2["fused"])
+    with pytest.raises(L.VFuseError):                              # more tokens than position embeddings
+        L.embed_pos_concat(dev(torch.zeros((1, 40), dtype=torch.long)), dev(p2["tok"]), dev(p2["pos"]), torch.zeros((1, 45, 64), device="cuda"), 5)
+
+
+@pytest.mark.parametrize("B,S,H,hd", [(3, 65, 8, 32), (2, 197, 3, 32), (1, 300, 2, 128), (2, 50, 4, 96)])
+def test_attention_other_head_dims(L, B, S, H, hd):
+    """vf_attention_fwd_hd: head dims the tcgen05 kernel is not built for (TINY_VIT_CONFIG: 8 heads of 32, S = 65)."""
+    qkv = bf(rnd(B * S, 3 * H * hd, seed=40))
+    out = torch.full((B * S, H * hd), float("nan"), dtype=torch.bfloat16, device="cuda")
+    L.attention(dev(qkv), out, B, S, H, hd ** -0.5, head_dim=hd)
+    q, k, v = (qkv.float().view(B, S, 3, H, hd)[:, :, i].transpose(1, 2) for i in range(3))
+    ref = (torch.softmax(q @ k.transpose(-1, -2) * hd ** -0.5, -1) @ v).transpose(1, 2).reshape(B * S, H * hd)
+    check_close(out, ref, tol=4e-3, what=f"attention head_dim {hd} S={S}")
+    with pytest.raises(L.VFuseError):
+        L.attention(dev(bf(rnd(4, 3 * 20, seed=1))), torch.zeros((4, 20), dtype=torch.bfloat16, device="cuda"), 1, 4, 1, 1.0, head_dim=20)
+
+
+def test_tiny_vit_dims_golden(golden_part2):
+    """A ViT at the TINY_VIT_CONFIG dims (4x4 patches -> vf_im2col_patches + GEMM, head_dim 32 -> CUDA-core attention,
+    10-class head -> scalar epilogue) against the live reference's output."""
+    from llm_quest_b200.multimodal.vision_transformer.vit_model import ViTModel
+
+    tv = golden_part2["tiny_vit"]
+    m = ViTModel(tv["cfg"])
+    m.load_state_dict({k: v.float() for k, v in tv["state_dict"].items()})
+    m = m.cuda().eval()
+    img = tv["images"].float().cuda()
+    with torch.inference_mode():
+        check_close(m(img, output_hidden_states=True), tv["hidden"], what="tiny-config ViT hidden vs reference")
+        check_close(m(img), tv["logits"], what="tiny-config ViT logits vs reference")
+        emb = m.patch_embedding(img)                                # PatchEmbedding2D.forward on its own
+    ref_emb = VO.patch_embed3d(tv["images"].float().unsqueeze(2), tv["state_dict"]["patch_embedding.conv_proj.weight"].float().unsqueeze(2),
+                               tv["state_dict"]["patch_embedding.conv_proj.bias"].float())
+    ref_emb = torch.cat([tv["state_dict"]["patch_embedding.cls_token"].float().expand(4, -1, -1), ref_emb], 1)
+    check_close(emb, ref_emb, tol=2e-3, what="PatchEmbedding2D with 4x4 patches")

@@ -128,17 +128,16 @@ def _random_qwen_sd(model, seed=123):
     return sd
 
 
-@pytest.mark.parametrize("px,T,B,ln_fuse", [(448, 2, 2, None), (224, 4, 1, None), (448, 2, 2, "0"), (448, 2, 2, "1")])
-def test_qwen_tower_full_size_vs_oracle(px, T, B, ln_fuse, monkeypatch):
-    """cfg-2 / cfg-4 shapes with the batch reduced to what the CPU oracle finishes in seconds. ln_fuse: every
+@pytest.mark.parametrize("px,T,B,ln_fold", [(448, 2, 2, 2), (224, 4, 1, 2), (448, 2, 2, 0), (448, 2, 2, 1)])
+def test_qwen_tower_full_size_vs_oracle(px, T, B, ln_fold):
+    """cfg-2 / cfg-4 shapes with the batch reduced to what the CPU oracle finishes in seconds. ln_fold: every
     LayerNorm placement (norm1 and norm2 folded into the GEMMs (default) / stand-alone kernels / norm1 folded only)."""
     from llm_quest_b200.qwen.qwen3_5.qwen3_5_vision_model import Qwen3_5VisionModel
 
-    if ln_fuse is not None:
-        monkeypatch.setenv("VF_LN_FUSE", ln_fuse)
     cfg = qwen_cfg(px)
     torch.manual_seed(123)
     m = Qwen3_5VisionModel(cfg).eval()
+    m.ln_fold = ln_fold
     sd = _random_qwen_sd(m)
     m.load_state_dict(sd)
     g = torch.Generator().manual_seed(1234)
@@ -148,7 +147,89 @@ def test_qwen_tower_full_size_vs_oracle(px, T, B, ln_fuse, monkeypatch):
         ref = VO.qwen_vision_forward(sd, cfg, pixels)
         out = m.cuda()(pixels.cuda())
     assert out.shape == (B, (T // 2) * (px // 32) ** 2, 1024)
-    check_close(out, ref, f"Qwen3-ViT tower {px}px T={T} ln_fuse={ln_fuse} vs fp32 oracle")
+    check_close(out, ref, f"Qwen3-ViT tower {px}px T={T} ln_fold={ln_fold} vs fp32 oracle")
+
+
+def test_qwen_tower_unrounded_fp32_weights_and_pixels_vs_oracle():
+    """The north-star tolerance is defined on the SAME random-init fp32 weights and fp32 pixels the reference sees:
+    nothing is pre-rounded to bf16 here — the oracle computes in fp32 on the un-rounded tensors, the B200 path rounds
+    its GEMM operands itself. cfg-2 shape, 12 layers, batch 2."""
+    from llm_quest_b200.qwen.qwen3_5.qwen3_5_vision_model import Qwen3_5VisionModel
+
+    cfg = qwen_cfg(448)
+    torch.manual_seed(123)
+    m = Qwen3_5VisionModel(cfg).eval()
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}          # fp32 as initialised
+    pixels = torch.randn(2, 3, 2, 448, 448, generator=torch.Generator().manual_seed(1234))   # fp32 randn
+    assert not torch.equal(pixels, pixels.to(torch.bfloat16).float())
+    with torch.inference_mode():
+        ref = VO.qwen_vision_forward(sd, cfg, pixels)
+        out = m.cuda()(pixels.cuda())
+    check_close(out, ref, "Qwen3-ViT tower 448px, un-rounded fp32 weights + pixels vs fp32 oracle")
+
+
+def test_vit_b16_unrounded_fp32_weights_vs_oracle():
+    from llm_quest_b200.multimodal.vision_transformer.vit_model import ViTModel
+
+    cfg = {"img_width": 224, "img_height": 224, "patch_size": 16, "num_channels": 3, "emb_dim": 768, "n_layers": 12,
+           "n_heads": 12, "drop_rate": 0.1, "qkv_bias": True, "num_classes": 100}
+    torch.manual_seed(123)
+    m = ViTModel(cfg).eval()
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    img = torch.randn(2, 3, 224, 224, generator=torch.Generator().manual_seed(1234))
+    with torch.inference_mode():
+        ref_h = VO.vit_forward(sd, cfg, img, output_hidden_states=True)
+        ref_l = VO.vit_forward(sd, cfg, img)
+        mc = m.cuda()
+        check_close(mc(img.cuda(), output_hidden_states=True), ref_h, "ViT-B/16 hidden, un-rounded fp32 weights vs fp32 oracle")
+        check_close(mc(img.cuda()), ref_l, "ViT-B/16 logits, un-rounded fp32 weights vs fp32 oracle")
+
+
+@pytest.mark.parametrize("px,T,what", [
+    (448, 8, "12 layers at S=3136 (cfg-3 forward()-native clip)"),
+    (448, 16, "12 layers at S=6272 (cfg-4 video)"),
+])
+def test_qwen_tower_long_sequences_full_depth_vs_oracle(px, T, what):
+    """Error accumulates over depth and the attention kernel keeps a stale row max (lazy rescale): the FULL 12-layer
+    tower at the long-sequence shapes, batch 1, un-rounded fp32 weights, against the fp32 oracle (tens of seconds of CPU)."""
+    from llm_quest_b200.qwen.qwen3_5.qwen3_5_vision_model import Qwen3_5VisionModel
+
+    cfg = qwen_cfg(px)
+    torch.manual_seed(123)
+    m = Qwen3_5VisionModel(cfg).eval()
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    pixels = torch.randn(1, 3, T, px, px, generator=torch.Generator().manual_seed(1234))
+    with torch.inference_mode():
+        ref = VO.qwen_vision_forward(sd, cfg, pixels)
+        out = m.cuda()(pixels.cuda())
+    check_close(out, ref, what)
+
+
+@pytest.mark.parametrize("offset", [10.0, 50.0])
+def test_qwen_tower_rows_with_large_mean_folded_layernorm(offset):
+    """Outlier rows: a position embedding that puts every token's mean `offset` standard deviations away from zero (real
+    ViT checkpoints carry such rows). The folded LayerNorms must hold the tolerance without any switch: the first
+    LayerNorm of the chain runs on the fp32 stream and every later producer subtracts the row's running mean before the
+    bf16 rounding (vf_epilogue.ln_shift)."""
+    from llm_quest_b200.qwen.qwen3_5.qwen3_5_vision_model import Qwen3_5VisionModel
+
+    cfg = qwen_cfg(224, vision_n_layers=4)
+    torch.manual_seed(123)
+    m = Qwen3_5VisionModel(cfg).eval()
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    g = torch.Generator().manual_seed(7)
+    sd["pos_embed.weight"] = sd["pos_embed.weight"] + offset * (1.0 + 0.2 * torch.randn(sd["pos_embed.weight"].shape[0], 1, generator=g))
+    m.load_state_dict(sd)
+    pixels = torch.randn(2, 3, 2, 224, 224, generator=torch.Generator().manual_seed(1234))
+    with torch.inference_mode():
+        ref = VO.qwen_vision_forward(sd, cfg, pixels)
+        mc = m.cuda()
+        assert mc.ln_fold == 2
+        out = mc(pixels.cuda())
+        mc.ln_fold = 0
+        out_plain = mc(pixels.cuda())
+    check_close(out, ref, f"tower with row means ~{offset} sigma, folded LayerNorms")
+    check_close(out_plain, ref, f"tower with row means ~{offset} sigma, stand-alone LayerNorms")
 
 
 def test_vit_b16_vs_oracle():
@@ -406,3 +487,239 @@ def test_graphed_encoder_matches_eager():
         assert torch.equal(out, r)
     with pytest.raises(ValueError):
         ge(xs[0][:1])
+
+
+def test_vision_cache_keys_on_tensor_identity_not_storage_address():
+    """a (data_ptr, shape, version) key lets the caching allocator hand the freed address of image A to image B
+    and the cache serve A's embeddings for B. The cache keeps image A's tensor alive and compares objects; an explicit
+    image_id overrides identity."""
+    from llm_quest_b200 import _lib
+    from llm_quest_b200.qwen.qwen3_5.qwen3_5_vlm_model import Qwen3_5VLM
+
+    px = 64
+    cfg = qwen_cfg(px, vision_n_layers=1, vocab_size=3000, image_token_id=2999)
+    torch.manual_seed(123)
+    vlm = Qwen3_5VLM(cfg).eval().cuda().enable_vision_cache()
+    ids = torch.randint(0, 1000, (1, 12))
+    ids[:, 3:7] = 2999
+    ids = ids.cuda()
+    g = torch.Generator().manual_seed(11)
+    with torch.inference_mode():
+        a = torch.randn(1, 3, 2, px, px, generator=g).cuda()
+        ea, _, _ = vlm.encode_and_fuse(ids, a)
+        addr = a.data_ptr()
+        del a                                            # without the cache's reference this block would be recycled
+        b = torch.randn(1, 3, 2, px, px, generator=g).cuda()
+        assert b.data_ptr() != addr, "the cached pixel tensor must stay alive"
+        _lib.reset_launch_count()
+        eb, _, _ = vlm.encode_and_fuse(ids, b)
+        assert _lib.launch_count() > 6 and not torch.equal(ea, eb), "a new image must miss"
+        _lib.reset_launch_count()
+        eb2, _, _ = vlm.encode_and_fuse(ids, b)
+        assert _lib.launch_count() <= 6 and torch.equal(eb, eb2), "the same tensor object must hit"
+        # explicit identity: same id hits whatever tensor carries the pixels, a new id misses
+        c = b.clone()
+        e1, _, _ = vlm.encode_and_fuse(ids, c, image_id="img-1")
+        _lib.reset_launch_count()
+        e2, _, _ = vlm.encode_and_fuse(ids, c.clone(), image_id="img-1")
+        assert _lib.launch_count() <= 6 and torch.equal(e1, e2)
+        _lib.reset_launch_count()
+        vlm.encode_and_fuse(ids, c, image_id="img-2")
+        assert _lib.launch_count() > 6
+
+
+def test_mrope_gated_attention_prefill_cfg3_sequence_vs_oracle():
+    """SURVEY §8f-1 at the cfg-3 sequence length: 2 x 2832 tokens, 8 query / 2 kv heads of 256, multimodal position ids
+    (the tiny fixture only covers seq 150). Oracle: fp32 restatement pinned to the reference module by the fixture."""
+    from llm_quest_b200.common.rope import RoPE
+    from llm_quest_b200.qwen.qwen3_5.qwen3_5_text_model import MRoPEGatedAttention
+
+    cfg = {"emb_dim": 1024, "n_heads": 8, "num_kv_groups": 2, "head_dim": 256, "dtype": torch.float32, "p_dropout": 0.0,
+           "training": False, "mrope_section": [11, 11, 10]}
+    torch.manual_seed(123)
+    att = MRoPEGatedAttention(cfg, layer_idx=3).eval()
+    with torch.no_grad():
+        att.q_norm.scale.add_(0.1 * torch.randn(256))
+        att.k_norm.scale.add_(0.1 * torch.randn(256))
+    sd = {k: v.detach().clone() for k, v in att.state_dict().items()}
+    b, seq = 2, 2832
+    g = torch.Generator().manual_seed(99)
+    x = torch.randn(b, seq, 1024, generator=g)
+    ids = torch.randint(0, 1000, (b, seq), generator=g)
+    for i in range(4):
+        ids[:, 410 + i * 606: 410 + i * 606 + 196] = IMG
+    pid = torch.from_numpy(FO.mrope_position_ids(ids.numpy(), [[1, 28, 28]] * 4, None, IMG, 2))
+    cos, sin = RoPE.compute_angles(10_000_000, 256, 8192, rotation_factor=0.25)
+    with torch.inference_mode():
+        ref = VO.mrope_gated_attention_forward(sd, cfg, x, cos, sin, pid)
+        out = att.cuda()(x.cuda(), None, cos, sin, position_ids=pid.cuda())
+    check_close(out, ref, "MRoPEGatedAttention prefill 2 x 2832 tokens vs fp32 oracle")
+
+
+def _reference():
+    """The unmodified reference (baseline/_ref, travels to the GPU box) or None."""
+    from baseline import ref
+
+    return ref if ref.available() else None
+
+
+def test_tiny_vit_config_vs_reference():
+    """TINY_VIT_CONFIG (config.py:175-186): 4x4 patches of 32x32 images (S = 65), emb 256, 8 heads of 32, 12 layers, 10
+    classes — the patch sizes / head dims the TMA gather GEMM and the tcgen05 attention are not built for run through
+    vf_im2col_patches + GEMM and the CUDA-core attention kernel. Checked against the live reference module when
+    baseline/_ref is present, else against the oracle restatement."""
+    from llm_quest_b200.multimodal.vision_transformer.vit_model import ViTModel
+
+    cfg = {"img_width": 32, "img_height": 32, "patch_size": 4, "num_channels": 3, "emb_dim": 256, "n_layers": 12, "n_heads": 8,
+           "drop_rate": 0.3, "qkv_bias": True, "num_classes": 10}
+    torch.manual_seed(123)
+    m = ViTModel(cfg).eval()
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    img = torch.randn(5, 3, 32, 32, generator=torch.Generator().manual_seed(1234))
+    R = _reference()
+    with torch.inference_mode():
+        if R is not None:
+            config = R.import_reference()
+            assert {k: config.TINY_VIT_CONFIG[k] for k in cfg} == cfg
+            rm = R.vit_model(config.TINY_VIT_CONFIG).eval()
+            rm.load_state_dict(sd)
+            ref_h, ref_l = rm(img, output_hidden_states=True), rm(img)
+        else:
+            ref_h, ref_l = VO.vit_forward(sd, cfg, img, output_hidden_states=True), VO.vit_forward(sd, cfg, img)
+        mc = m.cuda()
+        check_close(mc(img.cuda(), output_hidden_states=True), ref_h, "TINY_VIT_CONFIG hidden states")
+        check_close(mc(img.cuda()), ref_l, "TINY_VIT_CONFIG logits")
+
+
+def test_part2_text_half_and_concat_vs_reference():
+    """Part-2 fusion (vlm_engine.py:100-119): adapter(vit_hidden) ‖ get_embeddings(ids) in ONE pre-allocated buffer —
+    adapter rows through the GEMM's row remap, token + position embeddings by vf_embed_pos_concat. Reference:
+    get_embeddings + torch.cat from baseline/_ref when present, else the same two lines in torch."""
+    from llm_quest_b200.multimodal import vlm_engine as VE
+    from llm_quest_b200.multimodal.vision_transformer.vit_engine import ViTAdapter
+
+    torch.manual_seed(5)
+    b, n_vis, d_vit, d, seq, vocab, ctx = 3, 197, 768, 768, 40, 5000, 64
+
+    class GPT(torch.nn.Module):          # the two tables get_embeddings touches (gpt_model.py: emb_dict, pos_emb_dict)
+        def __init__(self):
+            super().__init__()
+            self.emb_dict = torch.nn.Embedding(vocab, d)
+            self.pos_emb_dict = torch.nn.Embedding(ctx, d)
+
+    gpt = GPT().eval()
+    ad = ViTAdapter(d_vit, d, adapter_type="ffn", hidden_size_factor=2).eval()
+    hid = torch.randn(b, n_vis, d_vit)
+    ids = torch.randint(0, vocab, (b, seq))
+    with torch.inference_mode():
+        R = _reference()
+        if R is not None:
+            R.import_reference()
+            from llm_quest.multimodal.vlm_engine import get_embeddings as ref_get
+
+            text_ref = ref_get(ids, gpt)
+        else:
+            text_ref = gpt.emb_dict(ids) + gpt.pos_emb_dict(torch.arange(seq))
+        vis_ref = VO.vit_adapter_forward({k: v.detach() for k, v in ad.state_dict().items()}, hid)
+        ref = torch.cat([vis_ref, text_ref], dim=1)
+        gpt, ad = gpt.cuda(), ad.cuda()
+        text = VE.get_embeddings(ids.cuda(), gpt)
+        fused, n = VE.fuse_vision_text(ad, hid.cuda(), ids.cuda(), gpt)
+    assert n == n_vis and fused.shape == (b, n_vis + seq, d)
+    assert torch.equal(text.cpu(), text_ref), "token + position embeddings are exact fp32 adds"
+    assert torch.equal(fused[:, n_vis:].cpu(), text_ref)
+    check_close(fused[:, :n_vis], vis_ref, "adapter rows of the fused buffer", tol=5e-3)
+    check_close(fused, ref, "Part-2 fused [vision | text] buffer", tol=5e-3)
+
+
+def test_standalone_gelu_and_rmsnorm_modules():
+    """GELU.forward (vit_transformer_block.py:43-44) and ZeroCenteredRMSNorm.forward (qwen3_next_attention.py:41-46)
+    as modules of their own."""
+    from llm_quest_b200.multimodal.vision_transformer.vit_transformer_block import GELU
+    from llm_quest_b200.qwen.qwen3_5.qwen3_5_text_model import ZeroCenteredRMSNorm
+
+    x = torch.randn(7, 33, 300, generator=torch.Generator().manual_seed(2)) * 3
+    with torch.inference_mode():
+        y = GELU()(x.cuda())
+        torch.testing.assert_close(y.cpu(), VO.gelu_erf(x), rtol=2e-6, atol=2e-6)
+        yb = GELU()(x.to(torch.bfloat16).cuda())
+        assert yb.dtype == torch.bfloat16
+        torch.testing.assert_close(yb.float().cpu(), VO.gelu_erf(x.to(torch.bfloat16).float()).to(torch.bfloat16).float(), rtol=1e-2, atol=1e-2)
+        for dt in (torch.float32, torch.bfloat16):
+            n = ZeroCenteredRMSNorm(256, dtype=dt)
+            with torch.no_grad():
+                n.scale.add_((0.2 * torch.randn(256)).to(dt))
+            xs = (torch.randn(4, 8, 50, 256, generator=torch.Generator().manual_seed(3)) * 2 + 0.3).to(dt)
+            ref = VO.zero_centered_rmsnorm(xs, n.scale.detach())
+            got = n.cuda()(xs.cuda())
+            assert got.dtype == dt and got.shape == xs.shape
+            if dt == torch.float32:
+                torch.testing.assert_close(got.cpu(), ref, rtol=2e-6, atol=2e-6)
+            else:   # one bf16 rounding of the same fp32 value: at most one ulp apart
+                assert (got.float().cpu() - ref.float()).abs().max() <= 2.0 ** -7 * ref.float().abs().max()
+
+
+def test_reference_vlm_forward_around_the_b200_tower():
+    """End-to-end drop-in proof: the reference's OWN Qwen3_5VLM.forward — embedding lookup,
+    masked_scatter, compute_3d_position_ids, text model — with only the vision tower replaced through shim.install(),
+    on the GPU, against the unmodified reference on the CPU. The tensors handed to the text model (fused embeddings,
+    position ids) are compared exactly / within the path tolerance; the logits loosely (the bf16 text model is the
+    reference's own code on both sides, GPU vs CPU arithmetic)."""
+    import importlib
+    import sys
+
+    import llm_quest_b200.shim as shim
+
+    R = _reference()
+    if R is None:
+        pytest.skip("baseline/_ref not installed (baseline/install_ref.sh)")
+    config = R.import_reference()
+    px = 64
+    over = {"n_layers": 4, "img_width": px, "img_height": px, "vision_n_layers": 2, "vocab_size": 3000, "image_token_id": 2999,
+            "context_length": 256}
+    cfg = {**config.QWEN3_5_08B_CONFIG, **over}
+    import llm_quest.qwen.qwen3_5.qwen3_5_vlm_model as ref_vlm_mod
+
+    ref_vlm_mod = importlib.reload(ref_vlm_mod)
+    torch.manual_seed(123)
+    ref_model = ref_vlm_mod.Qwen3_5VLM(dict(cfg)).eval()
+    assert type(ref_model.vision_model).__module__.startswith("llm_quest.")
+    sd = {k: v.detach().clone() for k, v in ref_model.state_dict().items()}
+    g = torch.Generator().manual_seed(4321)
+    b, T = 2, 4
+    n_vis = (T // 2) * (px // 32) ** 2
+    ids = torch.randint(0, 1000, (b, 40), generator=g)
+    ids[:, 7:7 + n_vis] = 2999
+    pixels = torch.randn(b, 3, T, px, px, generator=g)
+
+    def run(model, dev):
+        seen = {}
+        hook = model.language_model.register_forward_pre_hook(
+            lambda mod, args, kwargs: seen.update(embs=kwargs["inputs_embs"].detach().float().cpu(), pid=kwargs["position_ids"].detach().cpu()),
+            with_kwargs=True)
+        with torch.inference_mode():
+            logits = model(ids.to(dev), image_pixels=pixels.to(dev))
+        hook.remove()
+        return logits.float().cpu(), seen
+
+    ref_logits, ref_seen = run(ref_model, "cpu")
+    try:
+        shim.install(only=["llm_quest.qwen.qwen3_5.qwen3_5_vision_model"])
+        mod = importlib.reload(ref_vlm_mod)                     # the reference's module, now importing the B200 tower
+        torch.manual_seed(123)
+        model = mod.Qwen3_5VLM(dict(cfg)).eval()
+        assert type(model.vision_model).__module__.startswith("llm_quest_b200.")
+        assert mod.Qwen3_5VLM.forward.__code__.co_filename.endswith("baseline/_ref/llm_quest/qwen/qwen3_5/qwen3_5_vlm_model.py")
+        model.load_state_dict(sd)                               # same keys, same shapes: the reference's checkpoint loads
+        got_logits, got_seen = run(model.cuda(), "cuda")
+    finally:
+        shim.uninstall()
+        importlib.reload(ref_vlm_mod)
+    assert torch.equal(got_seen["pid"], ref_seen["pid"]), "position ids differ"
+    mask = (ids == 2999).view(-1)
+    ge, re_ = got_seen["embs"].view(-1, cfg["emb_dim"]), ref_seen["embs"].view(-1, cfg["emb_dim"])
+    assert torch.equal(ge[~mask], re_[~mask]), "text rows differ"
+    check_close(ge[mask], re_[mask], "vision rows handed to the reference's text model")
+    c = VO.cosine(got_logits, ref_logits)
+    print(f"logits of the reference VLM around the B200 tower vs the CPU reference: cosine {c:.6f}")
+    assert got_logits.shape == ref_logits.shape == (b, 40, 3000) and c >= 0.99

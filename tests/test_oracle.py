@@ -156,3 +156,22 @@ def test_text_attention_golden(golden_text_attention):
     assert VO.max_norm_err(got, g["expected"]) <= 2e-5
     got = VO.mrope_gated_attention_forward(sd, cfg, g["x"].float(), cos, sin, None)
     assert VO.max_norm_err(got, g["expected_1d"]) <= 2e-5
+
+
+def test_part2_tiny_goldens(golden_part2):
+    """Round-2 fixtures from the live reference: get_embeddings + concat (vlm_engine.py:5-20,114), a ViT at the
+    TINY_VIT_CONFIG dims (4x4 patches, head_dim 32), GELU.forward and ZeroCenteredRMSNorm.forward."""
+    g = golden_part2
+    p2 = g["part2"]
+    text = VO.get_embeddings(p2["ids"], p2["tok"], p2["pos"])
+    assert torch.equal(text, p2["text"]) and torch.equal(torch.cat([p2["vision"], text], 1), p2["fused"])
+    tv = g["tiny_vit"]
+    sd = {k: v.float() for k, v in tv["state_dict"].items()}
+    img = tv["images"].float()
+    assert tv["cfg"]["patch_size"] == 4 and tv["cfg"]["emb_dim"] // tv["cfg"]["n_heads"] == 32
+    assert VO.max_norm_err(VO.vit_forward(sd, tv["cfg"], img, output_hidden_states=True), tv["hidden"]) <= 2e-5
+    assert VO.max_norm_err(VO.vit_forward(sd, tv["cfg"], img), tv["logits"]) <= 2e-5
+    assert torch.equal(VO.gelu_erf(g["gelu"]["x"]), g["gelu"]["y"])
+    r = g["rmsnorm"]
+    assert torch.equal(VO.zero_centered_rmsnorm(r["x"], r["scale"]), r["y"])
+    assert torch.equal(VO.zero_centered_rmsnorm(r["x"].to(torch.bfloat16), r["scale"]), r["y_bf16"])
