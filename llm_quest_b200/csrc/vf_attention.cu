@@ -587,12 +587,14 @@ using namespace vf;
 static unsigned long long* g_trace_buf = nullptr;
 static int g_trace_first = 0, g_trace_n = 0;
 
-extern "C" int vf_attention_set_trace(void* buf, int32_t first_step, int32_t n_steps) {
+int vf_attention1_set_trace(void* buf, int32_t first_step, int32_t n_steps) {
   g_trace_buf = reinterpret_cast<unsigned long long*>(buf);
   g_trace_first = first_step;
   g_trace_n = buf ? n_steps : 0;
   return VF_OK;
 }
+
+int vf_attention2_launch(const void* qkv, void* out, int32_t B, int32_t S, int32_t H, float scale, void* stream);
 
 extern "C" int vf_attention_fwd(const void* qkv, void* out, int32_t B, int32_t S, int32_t H,
                                 float scale, void* stream) {
@@ -601,6 +603,14 @@ extern "C" int vf_attention_fwd(const void* qkv, void* out, int32_t B, int32_t S
   VF_REQUIRE((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
              VF_ERR_ALIGN, "vf_attention_fwd: pointers must be 16-byte aligned");
   VF_REQUIRE((long long)B * S < (1ll << 31), VF_ERR_ARG, "vf_attention_fwd: B*S too large");
+
+  // development A/B: VF_ATTN_V1=1 keeps the first design (four 128 x 64 chains); default = vf_attention2.cu
+  static int use_v1 = -1;
+  if (use_v1 < 0) {
+    const char* e1 = getenv("VF_ATTN_V1");
+    use_v1 = (e1 && e1[0] == '1') ? 1 : 0;
+  }
+  if (!use_v1) return vf_attention2_launch(qkv, out, B, S, H, scale, stream);
 
   AttnParams p{};
   p.B = B; p.S = S; p.H = H;
