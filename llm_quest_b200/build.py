@@ -23,7 +23,7 @@ BUILD = CSRC / "build"
 LIB = PKG_DIR / "libvfuse.so"
 INCLUDE = PKG_DIR.parent / "include"
 
-SOURCES = ["vf_api.cu", "vf_gemm.cu", "vf_attention.cu", "vf_attention2.cu", "vf_attention_gqa.cu", "vf_attention_small.cu", "vf_elementwise.cu", "vf_norm.cu", "vf_rope.cu", "vf_fuse.cu", "vf_preprocess.cu"]
+SOURCES = ["vf_api.cu", "vf_gemm.cu", "vf_attention.cu", "vf_attention_gqa.cu", "vf_attention_small.cu", "vf_elementwise.cu", "vf_norm.cu", "vf_rope.cu", "vf_fuse.cu", "vf_preprocess.cu"]
 ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

@@ -129,9 +129,14 @@ struct ItemIter {
   }
 };
 
+// (sample, head)-major with the query block fastest: the CTAs of the grid work on neighbouring items at any time, i.e. on
+// the query blocks of the same few (sample, head) pairs, so a pair's K/V tiles come from DRAM once and from L2 for its
+// other query blocks. (Round 1 walked all first blocks, then all second blocks, ...: every query block re-read K/V from
+// DRAM — 1.77x the algorithmic bytes at S = 784, ncu.) The snake walk below keeps the load balanced: the grid size is
+// even, so consecutive rounds hand a CTA items of alternating parity (full / ragged query block at S = 784).
 __device__ __forceinline__ void decode_item(const AttnParams& p, int item, int& b, int& h, int& qb) {
-  qb = item / p.n_bh;
-  const int bh = item - qb * p.n_bh;
+  const int bh = item / p.n_qblk;
+  qb = item - bh * p.n_qblk;
   b = bh / p.H;
   h = bh - b * p.H;
 }
@@ -587,14 +592,12 @@ using namespace vf;
 static unsigned long long* g_trace_buf = nullptr;
 static int g_trace_first = 0, g_trace_n = 0;
 
-int vf_attention1_set_trace(void* buf, int32_t first_step, int32_t n_steps) {
+extern "C" int vf_attention_set_trace(void* buf, int32_t first_step, int32_t n_steps) {
   g_trace_buf = reinterpret_cast<unsigned long long*>(buf);
   g_trace_first = first_step;
   g_trace_n = buf ? n_steps : 0;
   return VF_OK;
 }
-
-int vf_attention2_launch(const void* qkv, void* out, int32_t B, int32_t S, int32_t H, float scale, void* stream);
 
 extern "C" int vf_attention_fwd(const void* qkv, void* out, int32_t B, int32_t S, int32_t H,
                                 float scale, void* stream) {
@@ -603,14 +606,6 @@ extern "C" int vf_attention_fwd(const void* qkv, void* out, int32_t B, int32_t S
   VF_REQUIRE((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
              VF_ERR_ALIGN, "vf_attention_fwd: pointers must be 16-byte aligned");
   VF_REQUIRE((long long)B * S < (1ll << 31), VF_ERR_ARG, "vf_attention_fwd: B*S too large");
-
-  // development A/B: VF_ATTN_V1=1 keeps the first design (four 128 x 64 chains); default = vf_attention2.cu
-  static int use_v1 = -1;
-  if (use_v1 < 0) {
-    const char* e1 = getenv("VF_ATTN_V1");
-    use_v1 = (e1 && e1[0] == '1') ? 1 : 0;
-  }
-  if (!use_v1) return vf_attention2_launch(qkv, out, B, S, H, scale, stream);
 
   AttnParams p{};
   p.B = B; p.S = S; p.H = H;
