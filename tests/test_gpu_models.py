@@ -723,3 +723,51 @@ def test_reference_vlm_forward_around_the_b200_tower():
     c = VO.cosine(got_logits, ref_logits)
     print(f"logits of the reference VLM around the B200 tower vs the CPU reference: cosine {c:.6f}")
     assert got_logits.shape == ref_logits.shape == (b, 40, 3000) and c >= 0.99
+
+
+def test_hf_named_checkpoint_through_the_tower_vs_oracle():
+    """SURVEY §8f-4 on the GPU: a checkpoint under Hugging Face names (model.visual.*, built with the inverse of the
+    reference's own get_vision_remapping_rules when baseline/_ref is present) goes through load_qwen3_5_vision_weights
+    into the B200 tower; the forward must match the fp32 oracle run on the original tensors. Also the 3-D pre-extracted
+    patch branch of get_feeds_3d_shape (qwen3_5_vlm_model.py:77-81)."""
+    from llm_quest_b200.qwen.qwen3_5 import qwen3_5_weight_loading as WL
+    from llm_quest_b200.qwen.qwen3_5.qwen3_5_vision_model import Qwen3_5VisionModel
+    from llm_quest_b200.qwen.qwen3_5.qwen3_5_vlm_model import EmbeddingOnlyLM, Qwen3_5VLM
+
+    rules = WL.get_vision_remapping_rules()
+    R = _reference()
+    if R is not None:
+        R.import_reference()
+        from llm_quest.qwen.qwen3_5.qwen3_5_weight_loading import get_vision_remapping_rules as ref_rules
+
+        assert rules == ref_rules(), "the remapping table must equal the reference's"
+    cfg = qwen_cfg(224, vision_n_layers=3)
+    torch.manual_seed(321)
+    src = Qwen3_5VisionModel(cfg).eval()
+    sd = {k: v.detach().clone() for k, v in src.state_dict().items()}
+
+    def to_hf(k):
+        for hf, ours in rules:
+            if hf.startswith("model.visual.") and k.startswith(ours):
+                k = hf + k[len(ours):]
+                break
+        for hf, ours in rules:
+            if not hf.startswith("model.visual."):
+                k = k.replace(ours, hf)
+        return k
+
+    hf = {to_hf(k): v for k, v in sd.items()}
+    assert all(k.startswith("model.visual.") for k in hf) and "model.visual.blocks.2.mlp.linear_fc2.weight" in hf
+    hf["model.language_model.embed_tokens.weight"] = torch.zeros(4, 4)          # non-vision keys are ignored
+    torch.manual_seed(999)
+    dst = Qwen3_5VisionModel(cfg).eval()
+    missing, unexpected = WL.load_qwen3_5_vision_weights(dst, hf)
+    assert missing == [] and unexpected == []
+    pixels = torch.randn(2, 3, 2, 224, 224, generator=torch.Generator().manual_seed(1234))
+    with torch.inference_mode():
+        ref = VO.qwen_vision_forward(sd, cfg, pixels)
+        out = dst.cuda()(pixels.cuda())
+    check_close(out, ref, "tower loaded from an HF-named checkpoint vs fp32 oracle")
+    vlm = Qwen3_5VLM(cfg, language_model=EmbeddingOnlyLM({**cfg, "vocab_size": 64}))
+    assert vlm.get_feeds_3d_shape(torch.zeros(2, 3 * 196, 1536)).tolist() == [[3, 14, 14]]      # (b, num_patches, features)
+    assert vlm.get_feeds_3d_shape(pixels).tolist() == [[1, 14, 14]]
