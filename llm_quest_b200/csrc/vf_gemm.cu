@@ -150,7 +150,7 @@ template <int EPI, int BN, bool PATCH, int CG, bool RING = false>
 __global__ void __launch_bounds__(EpiCfg<EPI>::THREADS, 1)
 gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
             const __grid_constant__ CUtensorMap tmB, const __grid_constant__ EpiMaps em) {
-  static_assert(CG == 1 || (CG == 2 && BN == 256 && !PATCH), "CTA pairs: 256-wide tiles, plain A operand");
+  static_assert(CG == 1 || (CG == 2 && BN == 256), "CTA pairs: 256-wide tiles");
   static_assert(!RING || (EPI == VF_EPI_BIAS_RES_F32 && !PATCH && CG == 2), "the TMA ring belongs to the CTA-pair residual kernel");
   using L = SmemLayout<BN, CG, RING>;
   constexpr int STAGES = L::STAGES;
@@ -231,7 +231,8 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
             const int plane = kb / kb_per_plane;              // c*tp + dt
             const int py0 = (kb % kb_per_plane) * rows_per_kb;
             const int c = plane / p.tp, dt = plane % p.tp;
-            tma_load_5d(a_dst, &tmA, &full_bar[stage], 0, pc2, py0, pc3, pimg + c * p.T + dt);
+            if (CG == 2) tma_load_5d_pair(a_dst, &tmA, &full_bar[stage], 0, pc2, py0, pc3, pimg + c * p.T + dt);
+            else tma_load_5d(a_dst, &tmA, &full_bar[stage], 0, pc2, py0, pc3, pimg + c * p.T + dt);
           } else if (CG == 2) {
             tma_load_2d_pair(a_dst, &tmA, &full_bar[stage], kb * BK, m_blk * BM);
           } else {
@@ -263,8 +264,10 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
           const uint64_t b_desc = umma_desc_sw128(a_addr + L::A_BYTES);
           if (PATCH) {
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k)  // slice k = pixel row py0+k: [16 ph][8 pw][32 B], SBO 1024 B
-              umma_ss(d_tmem, umma_desc_sw32(a_addr + k * 256, 1024), b_desc + 2 * k, idesc, (kb | k) != 0);
+            for (int k = 0; k < BK / 16; ++k) {  // slice k = pixel row py0+k: [16 ph][8 pw][32 B], SBO 1024 B
+              if (CG == 2) umma_ss_pair(d_tmem, umma_desc_sw32(a_addr + k * 256, 1024), b_desc + 2 * k, idesc, (kb | k) != 0);
+              else umma_ss(d_tmem, umma_desc_sw32(a_addr + k * 256, 1024), b_desc + 2 * k, idesc, (kb | k) != 0);
+            }
           } else {
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k) {
@@ -588,7 +591,7 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
             const int r_local = r0 + 4 * i;          // tile rows are a 16 x 8 rectangle of patches
             const int ph = phb * 16 + (r_local >> 3);
             const int pw = pwb * 8 + (r_local & 7);
-            const bool ok = ph < p.nh && pw < p.nw;
+            const bool ok = ph < p.nh && pw < p.nw && m_blk < p.num_m_blk;   // (pair mode: the last pair may lack its second row block)
             aux[i] = ok ? ph * p.nw + pw : 0;
             orow[i] = ok ? base + aux[i] : -1;
           }
@@ -1126,6 +1129,10 @@ extern "C" int vf_patch_embed(const void* pixels, int32_t B, int32_t C, int32_t 
   p.M = B * Tp * nh * nw; p.N = N; p.K = K;
   const int bn = N <= 128 ? 128 : 256;
   p.num_m_blk = B * Tp * p.n_phb * p.n_pwb;
+  // CTA pairs (two row blocks = two patch rectangles per 256 x 256 tile, each CTA stages half of the W tile): a single CTA
+  // pulls 48 KB of operands per 512 tensor cycles through L2 -> SM (96 B/clk, above what the fabric delivers per SM: 610-670 TF),
+  // a pair 32 KB
+  const int cg = (bn == 256 && p.num_m_blk >= 2) ? 2 : 1;
   p.num_n_blk = (N + bn - 1) / bn;
   p.num_kb = K / BK;
   p.bias = bias;
@@ -1146,12 +1153,13 @@ extern "C" int vf_patch_embed(const void* pixels, int32_t B, int32_t C, int32_t 
   {
     uint64_t dims[2] = {(uint64_t)K, (uint64_t)N};
     uint64_t strides[1] = {(uint64_t)K * 2};
-    uint32_t box[2] = {BK, (uint32_t)bn};
+    uint32_t box[2] = {BK, (uint32_t)(bn / cg)};
     int e = encode_tmap(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, weight, dims, strides, box,
                         CU_TENSOR_MAP_SWIZZLE_128B);
     if (e) return e;
   }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (cg == 2) return launch_gemm<VF_EPI_BIAS_F32, 256, true, 2>(p, tmA, tmB, s);
   return bn == 256 ? launch_gemm<VF_EPI_BIAS_F32, 256, true>(p, tmA, tmB, s)
                    : launch_gemm<VF_EPI_BIAS_F32, 128, true>(p, tmA, tmB, s);
 }
