@@ -103,7 +103,7 @@ typedef struct {
    * to ln_xb_out (the next GEMM's A operand) and, per 32-column block j, the partial row sums
    * ln_stat_out[j * ln_stat_ld + row] = (sum x', sum x'^2) as float2 — N/32 partials per row, no atomics, fixed order.
    * vf_ln_row_stats() turns the partials into (mean', rstd) per row and advances the shift to the row's true mean.
-   * CONSUMER side (VF_EPI_GELU_*_BF16, VF_EPI_QKV_ROPE_BF16; N % 32 == 0): ln_row_stats holds (mean', rstd) of every row
+   * CONSUMER side (VF_EPI_BIAS_BF16, VF_EPI_GELU_*_BF16, VF_EPI_QKV_ROPE_BF16; N % 32 == 0): ln_row_stats holds (mean', rstd) of every row
    * of A; the epilogue applies the identity above with ln_colsum [N] fp32. `bias` must already hold b + W beta and W
    * must already be gamma-scaled (host side, once per weight). */
   void* ln_xb_out;           /* bf16 [rows, ln_ldxb] or NULL */
@@ -112,7 +112,17 @@ typedef struct {
   int64_t ln_stat_ld;        /* rows per partial plane (>= M) */
   const float* ln_shift;     /* fp32 [M] row shifts or NULL (= 0) */
   const void* ln_row_stats;  /* float2 [M] (mean', rstd) or NULL */
-  const float* ln_colsum;    /* [N] fp32 (required with ln_row_stats) */
+  const float* ln_colsum;    /* [N] fp32 (required with ln_row_stats / ln_part_in) */
+  /* CONSUMER, small problems: instead of ln_row_stats give the producer's partial sums (ln_part_in = its ln_stat_out,
+   * K/32 planes of ln_stat_ld rows) and the launch of vf_ln_row_stats in between is dropped: every epilogue warp adds up
+   * the partials of its 32 rows itself, in vf_ln_row_stats' summation order (same bits), eps = ln_eps, ln_variant as in
+   * vf_ln_row_stats; the first column tile of every row block advances ln_shift_update[row] by mean' (may be NULL). Every
+   * column tile re-reads the partials, so this only pays while the launch costs more than K/32 x 8 bytes per row and
+   * column tile (M up to a few thousand rows). */
+  const void* ln_part_in;    /* float2 [K/32][ln_stat_ld] or NULL */
+  float* ln_shift_update;    /* fp32 [M] or NULL */
+  float ln_eps;
+  int32_t ln_variant;
 } vf_epilogue;
 
 int vf_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, int32_t M, int32_t N,

@@ -64,6 +64,10 @@ class vf_epilogue(C.Structure):
         ("ln_shift", C.c_void_p),
         ("ln_row_stats", C.c_void_p),
         ("ln_colsum", C.c_void_p),
+        ("ln_part_in", C.c_void_p),
+        ("ln_shift_update", C.c_void_p),
+        ("ln_eps", C.c_float),
+        ("ln_variant", C.c_int32),
     ]
 
 
@@ -217,7 +221,8 @@ def gemm(a, w, mode, out, bias=None, res=None, rope=None, dst_rows=None, grp_row
     ln_out = (xb bf16 [rows, N], stat fp32 [N/32, rows, 2][, shift fp32 [rows]]): LayerNorm producer side (bias_res_f32
     only): bf16 copy and partial sums of the rows minus their shift.
     ln_in = (row_stats fp32 [M, 2] (mean', rstd) from ln_row_stats(), colsum fp32 [N]): LayerNorm consumer side
-    (GELU / QKV+RoPE epilogues); `w` and `bias` must be the folded ones (qwen3_5_vision_model._fold_ln)."""
+    (GELU / QKV+RoPE epilogues); `w` and `bias` must be the folded ones (qwen3_5_vision_model._fold_ln). Small problems:
+    ln_in = (partials fp32 [K/32, rows, 2], colsum, eps, variant, shift or None) — the launch adds the partials up itself."""
     _require_cuda(a, w, out, bias, res, dst_rows)
     assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and a.dim() == 2 and w.dim() == 2
     assert a.stride(1) == 1 and w.stride(1) == 1 and out.stride(-1) == 1
@@ -259,11 +264,23 @@ def gemm(a, w, mode, out, bias=None, res=None, rope=None, dst_rows=None, grp_row
             assert shift.dtype == torch.float32 and shift.is_contiguous() and shift.numel() >= M
             ep.ln_shift = shift.data_ptr()
     if ln_in is not None:
-        row_stats, colsum = ln_in
-        _require_cuda(row_stats, colsum)
-        assert row_stats.dtype == torch.float32 and row_stats.is_contiguous() and row_stats.shape == (M, 2)
+        colsum = ln_in[1]
+        _require_cuda(colsum)
         assert colsum.dtype == torch.float32 and colsum.is_contiguous() and colsum.numel() == N
-        ep.ln_row_stats, ep.ln_colsum = row_stats.data_ptr(), colsum.data_ptr()
+        ep.ln_colsum = colsum.data_ptr()
+        if len(ln_in) == 2:      # (row_stats, colsum): statistics finished by ln_row_stats()
+            row_stats = ln_in[0]
+            _require_cuda(row_stats)
+            assert row_stats.dtype == torch.float32 and row_stats.is_contiguous() and row_stats.shape == (M, 2)
+            ep.ln_row_stats = row_stats.data_ptr()
+        else:                    # (partials, colsum, eps, variant, shift or None): small problems, no launch in between
+            part, _, eps, variant, shift = ln_in
+            _require_cuda(part, shift)
+            assert part.dtype == torch.float32 and part.is_contiguous() and part.dim() == 3 and part.shape[0] == K // 32 and part.shape[2] == 2
+            ep.ln_part_in, ep.ln_stat_ld, ep.ln_eps, ep.ln_variant = part.data_ptr(), part.shape[1], float(eps), int(variant)
+            if shift is not None:
+                assert shift.dtype == torch.float32 and shift.is_contiguous() and shift.numel() >= M
+                ep.ln_shift_update = shift.data_ptr()
     with _timed("gemm_" + _EPI_NAMES.get(mode, str(mode)), flops=2.0 * M * N * K):
         check(lib().vf_gemm_bf16(a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), M, N, K, C.byref(ep),
                                  _stream()), "vf_gemm_bf16")

@@ -84,6 +84,11 @@ struct GemmParams {
   const float* ln_shift;     // producer: [M] per-row shift (an estimate of the row mean) or nullptr
   const float2* ln_row_stats;  // consumer: [M] (mean of the shifted row, rstd)
   const float* ln_colsum;      // consumer: [N]
+  // consumer, small problems: the producer's partial sums instead of finished statistics (no vf_ln_row_stats launch)
+  const float2* ln_part_in;    // [K/32][ln_stat_ld]
+  float* ln_shift_rw;          // [M] or nullptr: advanced to the rows' means by the first column tile of every row block
+  float ln_eps;
+  int ln_variant;
 };
 
 // CG = 1: one CTA per 128 x BN tile. CG = 2: a CTA pair (cta_group::2) per 256 x BN tile — each CTA stages
@@ -331,15 +336,41 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
                    : "memory");
     };
 
-    // Folded LayerNorm, consumer side: (mean, rstd) per row are final when the launch starts (vf_ln_row_stats between the
-    // producing and the consuming GEMM); lane L fetches the pair of tile row L.
-    [[maybe_unused]] auto ln_fetch = [&](int row_first, float& mu, float& rs) {
+    // Folded LayerNorm, consumer side: lane L fetches (mean', rstd) of tile row L. Normally they are final when the launch
+    // starts (vf_ln_row_stats between the producing and the consuming GEMM). For SMALL problems (ln_part_in) the launch
+    // in between is dropped: every epilogue warp adds up the K/32 partial sums of its 32 rows itself — in exactly
+    // vf_ln_row_stats' order (eight interleaved groups, then the groups in order), so a row's statistics do not depend on
+    // which of the two routes its batch size selects — and the first column tile of a row block advances the row shift.
+    [[maybe_unused]] auto ln_fetch = [&](int row_first, int n_blk, float& mu, float& rs) {
       mu = 0.f; rs = 0.f;
       const int row = row_first + lane;
-      if (row < p.M) {
+      if (row >= p.M) return;
+      if (p.ln_part_in == nullptr) {
         const float2 t = __ldg(p.ln_row_stats + row);
         mu = t.x; rs = t.y;
+        return;
       }
+      const int parts = p.K >> 5;
+      float gs[8], gq[8];
+#pragma unroll
+      for (int g = 0; g < 8; ++g) { gs[g] = 0.f; gq[g] = 0.f; }
+      for (int j0 = 0; j0 < parts; j0 += 8) {
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          if (j0 + g < parts) {
+            const float2 t = __ldcg(p.ln_part_in + (long long)(j0 + g) * p.ln_stat_ld + row);
+            gs[g] += t.x; gq[g] += t.y;
+          }
+        }
+      }
+      float s_ = gs[0], q_ = gq[0];
+#pragma unroll
+      for (int g = 1; g < 8; ++g) { s_ += gs[g]; q_ += gq[g]; }
+      const float inv_d = 1.0f / static_cast<float>(p.K);
+      mu = s_ * inv_d;
+      const float var = fmaxf(fmaf(-mu, mu, q_ * inv_d), 0.f);
+      rs = p.ln_variant == 0 ? rsqrtf(var + p.ln_eps) : 1.0f / (sqrtf(var) + p.ln_eps);
+      if (p.ln_shift_rw != nullptr && n_blk == 0 && chalf == 0) p.ln_shift_rw[row] += mu;
     };
 
     // Residual epilogue: the fp32 residual slab of a tile (128 KB) is pulled into L2 one tile ahead, while
@@ -492,13 +523,13 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
       if (p.out_tma) {
         ring_done = true;
         const uint32_t slots = smem_u32(smem + L::EPI_OFF + (warp - 2) * 4096);   // two 2 KB slots per warp
-        const bool ln_fold = p.ln_row_stats != nullptr;
+        const bool ln_fold = p.ln_row_stats != nullptr || p.ln_part_in != nullptr;
         int sl = 0;
         for (int tile = tile0; tile < num_tiles; tile += tile_step) {
           const int col0 = (tile % p.num_n_blk) * BN + chalf * COLS_PER_WARP;
           const int row0 = ((tile / p.num_n_blk) * CG + rank) * BM + quarter * 32;
           float mu = 0.f, rs = 1.f;
-          if (ln_fold) ln_fetch(row0, mu, rs);
+          if (ln_fold) ln_fetch(row0, tile % p.num_n_blk, mu, rs);
           wait_or_trap(&tfull_bar[acc], acc_phase);
           tc_fence_after();
           const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + chalf * COLS_PER_WARP;
@@ -644,9 +675,9 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
       // LayerNorm folded into this GEMM (consumer side): lane L fetches (mean, rstd) of tile row quarter*32 + L while the
       // tensor pipe is still busy with the tile; the coalesced mapping below gets the values of its rows by shuffle.
       [[maybe_unused]] float ln_mu = 0.f, ln_rs = 0.f;
-      [[maybe_unused]] const bool ln_in = p.ln_row_stats != nullptr;
-      if constexpr (EPI == VF_EPI_GELU_TANH_BF16 || EPI == VF_EPI_GELU_ERF_BF16 || EPI == VF_EPI_QKV_ROPE_BF16) {
-        if (ln_in) ln_fetch(m_blk * BM + quarter * 32, ln_mu, ln_rs);
+      [[maybe_unused]] const bool ln_in = p.ln_row_stats != nullptr || p.ln_part_in != nullptr;
+      if constexpr (EPI == VF_EPI_BIAS_BF16 || EPI == VF_EPI_GELU_TANH_BF16 || EPI == VF_EPI_GELU_ERF_BF16 || EPI == VF_EPI_QKV_ROPE_BF16) {
+        if (ln_in) ln_fetch(m_blk * BM + quarter * 32, n_blk, ln_mu, ln_rs);
       }
 
       wait_or_trap(&tfull_bar[acc], acc_phase);
@@ -751,7 +782,7 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
             float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
             if (p.bias) bv = __ldg(reinterpret_cast<const float4*>(p.bias + cc));
             [[maybe_unused]] float4 csv = make_float4(0.f, 0.f, 0.f, 0.f);
-            if constexpr (EPI == VF_EPI_GELU_TANH_BF16 || EPI == VF_EPI_GELU_ERF_BF16)
+            if constexpr (EPI == VF_EPI_BIAS_BF16 || EPI == VF_EPI_GELU_TANH_BF16 || EPI == VF_EPI_GELU_ERF_BF16)
               if (ln_in) csv = __ldg(reinterpret_cast<const float4*>(p.ln_colsum + cc));
             [[maybe_unused]] const bool ln_out = p.ln_xb != nullptr;
             // residual / pos-embed values of all 8 rows are fetched up front: they may alias `out`, so
@@ -768,7 +799,7 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
               for (int i = 0; i < 8; ++i) {
                 const float4 x = read_staged(stA, rl + 4 * i);
                 float v[4] = {x.x + bv.x, x.y + bv.y, x.z + bv.z, x.w + bv.w};
-                if constexpr (EPI == VF_EPI_GELU_TANH_BF16 || EPI == VF_EPI_GELU_ERF_BF16) {
+                if constexpr (EPI == VF_EPI_BIAS_BF16 || EPI == VF_EPI_GELU_TANH_BF16 || EPI == VF_EPI_GELU_ERF_BF16) {
                   if (ln_in) {   // rstd * (acc - mean * colsum) + bias'
                     const float mu = __shfl_sync(0xffffffffu, ln_mu, rl + 4 * i);
                     const float rs = __shfl_sync(0xffffffffu, ln_rs, rl + 4 * i);
@@ -1027,9 +1058,11 @@ extern "C" int vf_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t l
     p.ln_shift = ep->ln_shift;
     VF_REQUIRE((reinterpret_cast<uintptr_t>(ep->ln_shift) & 3) == 0, VF_ERR_ALIGN, "vf_gemm_bf16: ln_shift must be 4-byte aligned");
   }
-  if (ep->ln_row_stats) {
-    VF_REQUIRE(ep->mode == VF_EPI_GELU_TANH_BF16 || ep->mode == VF_EPI_GELU_ERF_BF16 || ep->mode == VF_EPI_QKV_ROPE_BF16,
-               VF_ERR_ARG, "vf_gemm_bf16: ln_row_stats needs a GELU or QKV+RoPE epilogue");
+  if (ep->ln_row_stats || ep->ln_part_in) {
+    VF_REQUIRE(!(ep->ln_row_stats && ep->ln_part_in), VF_ERR_ARG, "vf_gemm_bf16: give ln_row_stats OR ln_part_in, not both");
+    VF_REQUIRE((ep->mode == VF_EPI_BIAS_BF16 && ep->n_peers == 0) || ep->mode == VF_EPI_GELU_TANH_BF16 ||
+                   ep->mode == VF_EPI_GELU_ERF_BF16 || ep->mode == VF_EPI_QKV_ROPE_BF16,
+               VF_ERR_ARG, "vf_gemm_bf16: the folded LayerNorm (consumer) needs a bf16 bias / GELU / QKV+RoPE epilogue");
     VF_REQUIRE(ep->ln_colsum, VF_ERR_ARG, "vf_gemm_bf16: folded LayerNorm (consumer) needs ln_colsum");
     // N % 32: every 32-column block of a tile is entirely inside or outside the matrix, so no lane of an epilogue warp
     // leaves the block loop while the others still exchange (mean, rstd) by shuffle
@@ -1038,6 +1071,16 @@ extern "C" int vf_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t l
                VF_ERR_ALIGN, "vf_gemm_bf16: folded LayerNorm (consumer) needs aligned rows and N %% 32 == 0");
     p.ln_row_stats = static_cast<const float2*>(ep->ln_row_stats);
     p.ln_colsum = ep->ln_colsum;
+    if (ep->ln_part_in) {
+      VF_REQUIRE((K % 32) == 0 && ep->ln_stat_ld >= M && (reinterpret_cast<uintptr_t>(ep->ln_part_in) & 7) == 0 &&
+                     (ep->ln_variant == 0 || ep->ln_variant == 1),
+                 VF_ERR_ARG, "vf_gemm_bf16: ln_part_in needs K %% 32 == 0, ln_stat_ld >= M and ln_variant 0 / 1");
+      p.ln_part_in = static_cast<const float2*>(ep->ln_part_in);
+      p.ln_stat_ld = ep->ln_stat_ld;
+      p.ln_shift_rw = ep->ln_shift_update;
+      p.ln_eps = ep->ln_eps;
+      p.ln_variant = ep->ln_variant;
+    }
   }
 
   // CTA pairs for every 256-wide problem with at least one full pair of row blocks

@@ -45,13 +45,34 @@ class ViTMultiHeadAttention(nn.Module):
     def packed_out(self):
         return _w_bf16(self._packed, "wo", self.out_proj.weight), _f32(self._packed, "bo", self.out_proj.bias)
 
-    def attend(self, h2d, B, S):
-        """h2d bf16 [B*S, d_in] -> context bf16 [B*S, d_out]."""
+    def packed_qkv_folded(self, norm):
+        """Packed [3D, D] QKV weight with the LayerNorm in front of it folded in (see _fold_ln): (bf16 gamma-scaled weight,
+        fp32 folded bias, fp32 colsum of the rounded weight)."""
+        ws = [self.w_queries.weight, self.w_keys.weight, self.w_values.weight]
+        bs = [self.w_queries.bias, self.w_keys.bias, self.w_values.bias]
+
+        def build():
+            w = torch.cat([t.detach().float() for t in ws], 0)
+            wf = (w * norm.scale.detach().float()[None, :]).to(torch.bfloat16).contiguous()
+            b = w @ norm.shift.detach().float()
+            if bs[0] is not None:
+                b = b + torch.cat([t.detach().float() for t in bs], 0)
+            return wf, b.contiguous(), wf.float().sum(dim=1).contiguous()
+
+        return self._packed.get("wqkv_folded", ws + [t for t in bs if t is not None] + [norm.scale, norm.shift], build)
+
+    def attend(self, h2d, B, S, folded_norm=None, ln_in_fn=None):
+        """h2d bf16 [B*S, d_in] -> context bf16 [B*S, d_out]. folded_norm / ln_in_fn: the LayerNorm in front is folded into
+        the QKV GEMM (h2d is then the shifted bf16 copy of the un-normalised stream; ln_in_fn(norm, colsum) -> ln_in)."""
         if self.head_dim % 8 != 0 or self.head_dim > 128:
             raise VFuseError(f"vf_attention_fwd_hd takes head dims that are multiples of 8 up to 128, got {self.head_dim}")
-        w, b = self.packed_qkv()
         qkv = torch.empty((B * S, 3 * self.d_out), dtype=torch.bfloat16, device=h2d.device)
-        _lib.gemm(h2d, w, VF_EPI_BIAS_BF16, qkv, bias=b)
+        if folded_norm is not None:
+            wf, bf_, cs = self.packed_qkv_folded(folded_norm)
+            _lib.gemm(h2d, wf, VF_EPI_BIAS_BF16, qkv, bias=bf_, ln_in=ln_in_fn(folded_norm, cs))
+        else:
+            w, b = self.packed_qkv()
+            _lib.gemm(h2d, w, VF_EPI_BIAS_BF16, qkv, bias=b)
         ctx = torch.empty((B * S, self.d_out), dtype=torch.bfloat16, device=h2d.device)
         _lib.attention(qkv, ctx, B, S, self.num_heads, self.att_scaling, head_dim=self.head_dim)
         return ctx

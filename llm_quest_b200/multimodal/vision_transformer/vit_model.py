@@ -85,18 +85,26 @@ class ViTModel(nn.Module):
         self.classifier = nn.Linear(cfg["emb_dim"], cfg["num_classes"])
         self._packed = _Packed()
 
+    ln_fold = True    # fold ln_1 / ln_2 of every block into the neighbouring GEMMs (plain attribute; False = stand-alone kernels)
+
     def forward(self, x, output_hidden_states=False):
         """x [b, C, H, W] -> logits [b, num_classes], or the final hidden states [b, N+1, D]."""
         _forward_only_guard(self)
         pos = _f32(self._packed, "pos", self.pos_embedding)[0]
         x2d, B, S = self.patch_embedding.embed_into(x, pos)
         D = x2d.shape[1]
+        rows = B * S
         work = {
-            "h": torch.empty((B * S, D), dtype=torch.bfloat16, device=x.device),
-            "g": torch.empty((B * S, 4 * D), dtype=torch.bfloat16, device=x.device),
+            "h": torch.empty((rows, D), dtype=torch.bfloat16, device=x.device),
+            "g": torch.empty((rows, 4 * D), dtype=torch.bfloat16, device=x.device),
         }
-        for block in self.transformer_blocks:
-            block.run_(x2d, B, S, work)
+        if self.ln_fold and D % 32 == 0:     # LayerNorms folded into the GEMMs around them (see ViTTransformerBlock.run_)
+            work["stat"] = torch.empty((D // 32, rows, 2), dtype=torch.float32, device=x.device)
+            work["rows"] = torch.empty((rows, 2), dtype=torch.float32, device=x.device)
+            work["shift"] = torch.empty((rows,), dtype=torch.float32, device=x.device)
+        last = len(self.transformer_blocks) - 1
+        for i, block in enumerate(self.transformer_blocks):
+            block.run_(x2d, B, S, work, ln1_pending=i > 0, emit_next=i < last)
         lw, lb = self.final_ln.packed()
         pdt = self.pos_embedding.dtype
         if output_hidden_states:

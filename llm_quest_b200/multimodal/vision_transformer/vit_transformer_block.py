@@ -14,7 +14,8 @@ import torch.nn as nn
 
 from ... import _lib
 from ..._lib import VF_EPI_BIAS_F32, VF_EPI_BIAS_RES_F32, VF_EPI_GELU_ERF_BF16
-from ...qwen.qwen3_5.qwen3_5_vision_model import _Packed, _as_2d_bf16, _f32, _forward_only_guard, _w_bf16
+from ...qwen.qwen3_5.qwen3_5_vision_model import (LN_STATS_IN_CONSUMER_MAX_ROWS, _Packed, _as_2d_bf16, _f32, _fold_ln,
+                                                    _forward_only_guard, _w_bf16)
 from .vit_attention import ViTMultiHeadAttention
 
 
@@ -98,19 +99,43 @@ class ViTTransformerBlock(nn.Module):
         self.ffn = FFN(cfg)
         self.dropout = nn.Dropout(cfg["drop_rate"])
 
-    def run_(self, x2d, B, S, work):
-        """In-place update of the fp32 residual stream x2d [B*S, D]."""
+    def run_(self, x2d, B, S, work, ln1_pending=False, emit_next=False):
+        """In-place update of the fp32 residual stream x2d [B*S, D].
+
+        With work["stat"] present the two LayerNorms (eps on the std: vf_ln_row_stats / ln_part_in variant 1) are folded
+        into the GEMMs around them exactly as in the Qwen tower (qwen3_5_vision_model.Qwen3_5VisionTransformerBlock.run_):
+        out_proj / ffn.layers.2 produce bf16(x - shift) and the partial row sums, the packed QKV GEMM / ffn.layers.0
+        consume them; the first LayerNorm of the chain runs stand-alone on the fp32 stream and yields the first shift."""
         l1w, l1b = self.ln_1.packed()
         l2w, l2b = self.ln_2.packed()
         w1, b1, w2, b2 = self.ffn.packed()
-        h, g = work["h"], work["g"]
-        _lib.layernorm(x2d, l1w, l1b, h, self.ln_1.eps, variant=1)
-        ctx = self.att.attend(h, B, S)
+        h, g, stat, rows, shift = work["h"], work["g"], work.get("stat"), work.get("rows"), work.get("shift")
+        D = x2d.shape[1]
+        fold = stat is not None
+        small = x2d.shape[0] <= LN_STATS_IN_CONSUMER_MAX_ROWS
+        c = self.att._packed
+
+        def consumer(norm, colsum):
+            if small:
+                return (stat, colsum, norm.eps, 1, shift)
+            _lib.ln_row_stats(stat, D, norm.eps, rows, shift, variant=1)
+            return (rows, colsum)
+
+        if fold and ln1_pending:
+            ctx = self.att.attend(h, B, S, folded_norm=self.ln_1, ln_in_fn=consumer)
+        else:
+            _lib.layernorm(x2d, l1w, l1b, h, self.ln_1.eps, variant=1, mean_out=shift if fold else None)
+            ctx = self.att.attend(h, B, S)
         wo, bo = self.att.packed_out()
-        _lib.gemm(ctx, wo, VF_EPI_BIAS_RES_F32, x2d, bias=bo, res=x2d)
-        _lib.layernorm(x2d, l2w, l2b, h, self.ln_2.eps, variant=1)
-        _lib.gemm(h, w1, VF_EPI_GELU_ERF_BF16, g, bias=b1)
-        _lib.gemm(g, w2, VF_EPI_BIAS_RES_F32, x2d, bias=b2, res=x2d)
+        producer = (h, stat, shift) if fold else None
+        _lib.gemm(ctx, wo, VF_EPI_BIAS_RES_F32, x2d, bias=bo, res=x2d, ln_out=producer)
+        if fold:
+            w1f, b1f, cs1 = _fold_ln(self.ffn._packed, "fold_l0", self.ffn.layers[0], self.ln_2)
+            _lib.gemm(h, w1f, VF_EPI_GELU_ERF_BF16, g, bias=b1f, ln_in=consumer(self.ln_2, cs1))
+        else:
+            _lib.layernorm(x2d, l2w, l2b, h, self.ln_2.eps, variant=1)
+            _lib.gemm(h, w1, VF_EPI_GELU_ERF_BF16, g, bias=b1)
+        _lib.gemm(g, w2, VF_EPI_BIAS_RES_F32, x2d, bias=b2, res=x2d, ln_out=producer if emit_next else None)
 
     def forward(self, x):
         _forward_only_guard(self)

@@ -76,22 +76,31 @@ def _f32(cache: _Packed, key, p):
     return cache.get(key, [p], lambda: p.detach().to(torch.float32).contiguous())
 
 
-def _fold_ln(cache: _Packed, key, lin: nn.Linear, norm: nn.LayerNorm):
+def _fold_ln(cache: _Packed, key, lin: nn.Linear, norm):
     """LayerNorm folded into the Linear that follows it:
         LN(x) @ W^T + b = rstd * (x @ (gamma . W)^T - mean * colsum) + (b + W beta)
     Returns (bf16 gamma-scaled weight, fp32 folded bias, fp32 colsum of the ROUNDED weight — the GEMM multiplies by
-    the rounded one, so the mean term must cancel against exactly that)."""
+    the rounded one, so the mean term must cancel against exactly that). `norm`: nn.LayerNorm (weight / bias) or the
+    Part-1 LayerNorm (scale / shift)."""
+    gamma = norm.weight if hasattr(norm, "weight") else norm.scale
+    beta = norm.bias if hasattr(norm, "bias") else norm.shift
 
     def build():
         w = lin.weight.detach().to(torch.float32)
-        wf = (w * norm.weight.detach().to(torch.float32)[None, :]).to(torch.bfloat16).contiguous()
+        wf = (w * gamma.detach().to(torch.float32)[None, :]).to(torch.bfloat16).contiguous()
         colsum = wf.to(torch.float32).sum(dim=1).contiguous()
-        b = w @ norm.bias.detach().to(torch.float32)
+        b = w @ beta.detach().to(torch.float32)
         if lin.bias is not None:
             b = b + lin.bias.detach().to(torch.float32)
         return wf, b.contiguous(), colsum
 
-    return cache.get(key, [lin.weight, lin.bias, norm.weight, norm.bias], build)
+    return cache.get(key, [lin.weight, lin.bias, gamma, beta], build)
+
+
+# Up to this many rows the consuming GEMM adds up the producer's partial row sums itself (vf_epilogue.ln_part_in) and the
+# vf_ln_row_stats launch in between is dropped: at small batches the launch costs more than the re-read of the partials by
+# every column tile (batch 1-4 of the Qwen tower, the Part-1 ViT at batch 8: 1576 rows). Same bits either way.
+LN_STATS_IN_CONSUMER_MAX_ROWS = 4096
 
 
 def _as_2d_bf16(x: torch.Tensor) -> torch.Tensor:
@@ -247,10 +256,17 @@ class Qwen3_5VisionTransformerBlock(nn.Module):
         h, g, stat, rows, shift = work["h"], work["g"], work.get("stat"), work.get("rows"), work.get("shift")
         D = x2d.shape[1]
         fold = stat is not None
+        small = x2d.shape[0] <= LN_STATS_IN_CONSUMER_MAX_ROWS
+
+        def consumer(eps, colsum):
+            if small:
+                return (stat, colsum, eps, 0, shift)
+            _lib.ln_row_stats(stat, D, eps, rows, shift)
+            return (rows, colsum)
+
         if fold and ln1_pending:
             wq, bq, csq = _fold_ln(c, "fold_qkv", self.att.qkv, self.norm1)
-            _lib.ln_row_stats(stat, D, self.norm1.eps, rows, shift)
-            ctx = self.att.attend(h, B, S, rope, folded=(wq, bq), ln_in=(rows, csq))
+            ctx = self.att.attend(h, B, S, rope, folded=(wq, bq), ln_in=consumer(self.norm1.eps, csq))
         else:
             n1w, n1b = _f32(c, "n1w", self.norm1.weight), _f32(c, "n1b", self.norm1.bias)
             _lib.layernorm(x2d, n1w, n1b, h, self.norm1.eps, mean_out=shift if fold else None)
@@ -259,8 +275,7 @@ class Qwen3_5VisionTransformerBlock(nn.Module):
         if fold and work.get("fold_norm2"):
             w1f, b1f, cs1 = _fold_ln(c, "fold_lin1", self.ffn.lin1, self.norm2)
             _lib.gemm(ctx, wo, VF_EPI_BIAS_RES_F32, x2d, bias=bo, res=x2d, ln_out=producer)
-            _lib.ln_row_stats(stat, D, self.norm2.eps, rows, shift)
-            _lib.gemm(h, w1f, VF_EPI_GELU_TANH_BF16, g, bias=b1f, ln_in=(rows, cs1))
+            _lib.gemm(h, w1f, VF_EPI_GELU_TANH_BF16, g, bias=b1f, ln_in=consumer(self.norm2.eps, cs1))
         else:
             n2w, n2b = _f32(c, "n2w", self.norm2.weight), _f32(c, "n2b", self.norm2.bias)
             _lib.gemm(ctx, wo, VF_EPI_BIAS_RES_F32, x2d, bias=bo, res=x2d)

@@ -271,13 +271,57 @@ def test_gemm_folded_layernorm_rows_with_large_mean(L, offset):
     assert errs[False] > 2 * errs[True], "the shift should matter for such rows"
 
 
+@pytest.mark.parametrize("mode,M", [("tanh", 1000), ("qkv", 1176), ("bias", 300)])
+def test_gemm_folded_layernorm_statistics_in_the_consumer_same_bits(L, mode, M):
+    """Small problems: the consuming GEMM adds up the producer's partial sums itself (ln_part_in) — bit for bit what the
+    vf_ln_row_stats route gives, including the advanced row shift; variant 1 (eps on the std) for the Part-1 LayerNorm."""
+    nh, nw = 7, 6
+    n = nh * nw
+    D = 768
+    N = 3 * D if mode == "qkv" else 1024
+    variant = 1 if mode == "bias" else 0
+    eps = 1e-5 if variant else 1e-6
+    a, w0, b0 = dev(bf(rnd(M, 128, seed=70))), dev(bf(rnd(D, 128, seed=71, scale=0.1))), dev(rnd(D, seed=72))
+    res = rnd(M, D, seed=73) * 2.0 + 3.0
+    gamma, beta = 1.0 + 0.2 * rnd(D, seed=74), 0.1 * rnd(D, seed=75)
+    w, b = rnd(N, D, seed=76, scale=0.05), rnd(N, seed=77)
+    wf, bfold, cs = (dev(t) for t in _fold(w, b, gamma, beta))
+    cos, sin = VO.axial_rope_tables(10_000, 64, nh, nw)
+    rope = (dev(cos[:, :32].contiguous()), dev(sin[:, :32].contiguous()), n, 2 * D)
+    epi = {"tanh": L.VF_EPI_GELU_TANH_BF16, "qkv": L.VF_EPI_QKV_ROPE_BF16, "bias": L.VF_EPI_BIAS_BF16}[mode]
+    outs, shifts = [], []
+    for in_consumer in (False, True):
+        x = dev(res.clone())
+        shift = dev(res.mean(1).contiguous())
+        xb = torch.empty((M, D), dtype=torch.bfloat16, device="cuda")
+        stat = torch.empty((D // 32, M, 2), device="cuda")
+        L.gemm(a, w0, L.VF_EPI_BIAS_RES_F32, x, bias=b0, res=x, ln_out=(xb, stat, shift))
+        out = torch.zeros((M, N), dtype=torch.bfloat16, device="cuda")
+        if in_consumer:
+            ln_in = (stat, cs, eps, variant, shift)
+        else:
+            rows = torch.empty((M, 2), device="cuda")
+            L.ln_row_stats(stat, D, eps, rows, shift, variant=variant)
+            ln_in = (rows, cs)
+        L.gemm(xb, wf, epi, out, bias=bfold, ln_in=ln_in, rope=rope if mode == "qkv" else None)
+        outs.append(out.cpu())
+        shifts.append(shift.cpu())
+    assert torch.equal(outs[0], outs[1]), "the two statistics routes differ"
+    assert torch.equal(shifts[0], shifts[1]), "the advanced row shifts differ"
+    xr = x.cpu()
+    torch.testing.assert_close(shifts[1], xr.mean(1), rtol=1e-5, atol=1e-4)
+    if mode == "bias":
+        ref = VO.std_layernorm(xr, gamma, beta, eps) @ w.t() + b
+        check_close(outs[1], ref, tol=6e-3, what="folded Part-1 LayerNorm -> plain bf16 epilogue")
+
+
 def test_gemm_folded_layernorm_rejects_bad_arguments(L):
     M, N, K = 256, 768, 768
     a, w = dev(bf(rnd(M, K, seed=80))), dev(bf(rnd(N, K, seed=81)))
     out = torch.zeros((M, N), dtype=torch.bfloat16, device="cuda")
     rows, cs = torch.zeros((M, 2), device="cuda"), torch.zeros(N, device="cuda")
     with pytest.raises(L.VFuseError):                         # epilogue without a folded-LN form
-        L.gemm(a, w, L.VF_EPI_BIAS_BF16, out, ln_in=(rows, cs))
+        L.gemm(a, w, L.VF_EPI_BIAS_F32, torch.zeros((M, N), device="cuda"), ln_in=(rows, cs))
     xf = torch.zeros((M, N), device="cuda")
     with pytest.raises(L.VFuseError):                         # producer needs the residual epilogue
         L.gemm(a, w, L.VF_EPI_BIAS_F32, xf, ln_out=(out, torch.zeros((N // 32, M, 2), device="cuda")))

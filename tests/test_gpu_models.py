@@ -232,23 +232,29 @@ def test_qwen_tower_rows_with_large_mean_folded_layernorm(offset):
     check_close(out_plain, ref, f"tower with row means ~{offset} sigma, stand-alone LayerNorms")
 
 
-def test_vit_b16_vs_oracle():
-    """cfg-1: Part-1 ViT-B/16, 224^2 (batch 2 of the 8)."""
+@pytest.mark.parametrize("fold,batch", [(True, 2), (False, 2), (True, 24)])
+def test_vit_b16_vs_oracle(fold, batch):
+    """cfg-1: Part-1 ViT-B/16, 224^2. fold: ln_1 / ln_2 folded into the GEMMs around them (default) or stand-alone kernels;
+    batch 24 = 4728 rows takes the vf_ln_row_stats route, batch 2 the statistics-in-the-consumer route (same bits per row)."""
     from llm_quest_b200.multimodal.vision_transformer.vit_model import ViTModel
 
     cfg = {"img_width": 224, "img_height": 224, "patch_size": 16, "num_channels": 3, "emb_dim": 768, "n_layers": 12,
            "n_heads": 12, "drop_rate": 0.1, "qkv_bias": True, "num_classes": 100}
     torch.manual_seed(123)
     m = ViTModel(cfg).eval()
+    m.ln_fold = fold
     sd = _random_qwen_sd(m)
     m.load_state_dict(sd)
-    img = torch.randn(2, 3, 224, 224, generator=torch.Generator().manual_seed(1234)).to(torch.bfloat16).float()
+    img = torch.randn(batch, 3, 224, 224, generator=torch.Generator().manual_seed(1234)).to(torch.bfloat16).float()
     with torch.inference_mode():
-        ref_h = VO.vit_forward(sd, cfg, img, output_hidden_states=True)
-        ref_l = VO.vit_forward(sd, cfg, img)
+        ref_h = VO.vit_forward(sd, cfg, img[:2], output_hidden_states=True)
+        ref_l = VO.vit_forward(sd, cfg, img[:2])
         mc = m.cuda()
-        check_close(mc(img.cuda(), output_hidden_states=True), ref_h, "ViT-B/16 hidden vs fp32 oracle")
-        check_close(mc(img.cuda()), ref_l, "ViT-B/16 logits vs fp32 oracle")
+        hid, logits = mc(img.cuda(), output_hidden_states=True), mc(img.cuda())
+        check_close(hid[:2], ref_h, f"ViT-B/16 hidden vs fp32 oracle (fold={fold}, batch {batch})")
+        check_close(logits[:2], ref_l, f"ViT-B/16 logits vs fp32 oracle (fold={fold}, batch {batch})")
+        if batch > 2 and fold:       # a sample's result does not depend on the statistics route its batch size selects
+            assert torch.equal(mc(img[:2].cuda(), output_hidden_states=True), hid[:2])
 
 
 def test_vlm_encode_and_fuse_vs_oracle():
