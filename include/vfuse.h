@@ -127,6 +127,9 @@ typedef struct {
 
 int vf_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, int32_t M, int32_t N,
                  int32_t K, const vf_epilogue* ep, void* stream);
+/* Diagnosis only: every following vf_gemm_bf16 launch writes, per CTA, {cycles of the MMA issuer's loop, cycles it waited
+ * for operands, cycles it waited for a free accumulator, tiles} into buf (device int64 [grid][4]); NULL switches it off. */
+int vf_gemm_set_debug(void* buf);
 
 /* ---------------------------------------------------------------------------------------------
  * Patch embedding as an im2col-free GEMM: the A operand is gathered by 5-D TMA boxes straight from

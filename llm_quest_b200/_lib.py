@@ -26,7 +26,7 @@ VF_EPI_QKV_ROPE_BF16 = 5
 VF_EPI_SCATTER_BF16 = 6
 
 EXPORTS = [
-    "vf_version", "vf_last_error", "vf_launch_count", "vf_launch_count_reset", "vf_gemm_bf16",
+    "vf_version", "vf_last_error", "vf_launch_count", "vf_launch_count_reset", "vf_gemm_bf16", "vf_gemm_set_debug",
     "vf_patch_embed", "vf_attention_fwd", "vf_attention_fwd_hd", "vf_attention_set_trace", "vf_attention_gqa_fwd", "vf_layernorm", "vf_ln_row_stats", "vf_vit_cls_pos", "vf_rope_apply",
     "vf_mrope_apply", "vf_mrope_apply_strided", "vf_mrope_position_ids", "vf_fuse_scan", "vf_embed_gather_scatter",
     "vf_cast_f32_to_bf16", "vf_cast_bf16_to_f32", "vf_preprocess_u8",
@@ -92,6 +92,7 @@ def lib() -> C.CDLL:
     L.vf_launch_count_reset.restype = None
     sigs = {
         "vf_gemm_bf16": [vp, i64, vp, i64, i32, i32, i32, C.POINTER(vf_epilogue), vp],
+        "vf_gemm_set_debug": [vp],
         "vf_patch_embed": [vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, i64, i32, vp, i64, i64, i64, vp],
         "vf_attention_fwd": [vp, vp, i32, i32, i32, f32, vp],
         "vf_attention_fwd_hd": [vp, vp, i32, i32, i32, i32, f32, vp],

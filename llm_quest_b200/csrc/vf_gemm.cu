@@ -89,6 +89,8 @@ struct GemmParams {
   float* ln_shift_rw;          // [M] or nullptr: advanced to the rows' means by the first column tile of every row block
   float ln_eps;
   int ln_variant;
+  long long* dbg;              // diagnosis (vf_gemm_set_debug): per CTA {issuer loop cycles, cycles waiting for operands,
+                               //   cycles waiting for a free accumulator, tiles}
 };
 
 // CG = 1: one CTA per 128 x BN tile. CG = 2: a CTA pair (cta_group::2) per 256 x BN tile — each CTA stages
@@ -257,12 +259,16 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      long long t_loop = 0, t_ops = 0, t_acc = 0, n_tiles = 0;
+      if (p.dbg) t_loop = clock64();
       for (int tile = tile0; tile < num_tiles; tile += tile_step) {
-        wait_or_trap(&tempty_bar[acc], acc_phase ^ 1);
+        if (p.dbg) { const long long c0 = clock64(); wait_or_trap(&tempty_bar[acc], acc_phase ^ 1); t_acc += clock64() - c0; ++n_tiles; }
+        else wait_or_trap(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb = 0; kb < p.num_kb; ++kb) {
-          wait_or_trap(&full_bar[stage], phase);
+          if (p.dbg) { const long long c0 = clock64(); wait_or_trap(&full_bar[stage], phase); t_ops += clock64() - c0; }
+          else wait_or_trap(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + stage * L::STAGE_BYTES);
           const uint64_t a_desc = umma_desc_sw128(a_addr);
@@ -290,6 +296,10 @@ gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA,
         if (CG == 2) umma_commit_pair(&tfull_bar[acc]);
         else umma_commit(&tfull_bar[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+      if (p.dbg) {
+        long long* d = p.dbg + 4ll * blockIdx.x;
+        d[0] = clock64() - t_loop; d[1] = t_ops; d[2] = t_acc; d[3] = n_tiles;
       }
     }
   } else {
@@ -985,6 +995,14 @@ static int pick_bn(int M, int N) {
 
 using namespace vf;
 
+static long long* g_gemm_dbg = nullptr;
+// Diagnosis: every following GEMM launch writes, per CTA, {cycles of the MMA issuer's loop, cycles it waited for operands
+// (full barriers), cycles it waited for a free accumulator (epilogue), tiles} into buf (int64 [grid][4]); NULL = off.
+extern "C" int vf_gemm_set_debug(void* buf) {
+  g_gemm_dbg = static_cast<long long*>(buf);
+  return VF_OK;
+}
+
 extern "C" int vf_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, int32_t M,
                             int32_t N, int32_t K, const vf_epilogue* ep, void* stream) {
   VF_REQUIRE(A && W && ep && ep->out, VF_ERR_ARG, "vf_gemm_bf16: null pointer");
@@ -1026,6 +1044,7 @@ extern "C" int vf_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t l
   p.rope_period = ep->rope_period; p.rope_cols = ep->rope_cols;
   p.dst_rows = ep->dst_rows;
   p.vec_ok = vec_ok ? 1 : 0;
+  p.dbg = g_gemm_dbg;
   p.n_peers = 0;
   if (ep->n_peers > 0) {
     VF_REQUIRE(ep->n_peers <= 8, VF_ERR_ARG, "vf_gemm_bf16: at most 8 peer buffers");
