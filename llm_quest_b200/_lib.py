@@ -165,7 +165,10 @@ class KernelTimer:
 
     active = None
 
-    def __init__(self):
+    def __init__(self, external: bool = False):
+        # external=True: events that may be recorded inside a CUDA-graph capture (they become event-record nodes; after a
+        # replay elapsed_time() gives the kernel's duration INSIDE the back-to-back step, at the step's clocks and cache state)
+        self.external = external
         self.records = []  # (kernel family, meta dict, start event, end event)
 
     def __enter__(self):
@@ -196,12 +199,12 @@ class _timed:
 
     def __enter__(self):
         if self.kt is not None:
-            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0 = torch.cuda.Event(enable_timing=True, external=self.kt.external)
             self.e0.record()
 
     def __exit__(self, *exc):
         if self.kt is not None:
-            e1 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True, external=self.kt.external)
             e1.record()
             self.kt.records.append((self.family, self.meta, self.e0, e1))
 
