@@ -27,7 +27,7 @@ if which == "all":
     print("cublas bf16 out                        : %.1f us" % t(lambda: torch.matmul(a, w.t(), out=ob)))
     xx = torch.empty_like(x)
     print("torch copy fp32 (154 in, 154 out)      : %.1f us" % t(lambda: xx.copy_(x)))
-print("res in place   (154 in + 154 out) VF_RES_TMA=%s : %.1f us" % (os.environ.get("VF_RES_TMA", "1"),
+print("res in place   (154 in + 154 out, TMA ring epilogue) : %.1f us" % (
       t(lambda: L.gemm(a, w, L.VF_EPI_BIAS_RES_F32, x, bias=b, res=x))))
 x2 = torch.empty_like(x)
 print("res out of place                                     : %.1f us" % t(lambda: L.gemm(a, w, L.VF_EPI_BIAS_RES_F32, x2, bias=b, res=x)))
