@@ -464,6 +464,10 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     _lib.lib()
 
+    # host side of the end-to-end path: this rank's pinned buffers should live on the NUMA node next to its GPU
+    from llm_quest_b200.pipeline import bind_host_thread_to_gpu_numa
+
+    numa = bind_host_thread_to_gpu_numa(local) if world > 1 else "single rank: not bound"
     wl = make_workload(args.workload, args.batch, args.cpu_batch)
     B = wl.B
     model = wl.build_ours(dev)
@@ -665,6 +669,7 @@ def run_ours(args):
             "e2e": {"value": round(e2e_value, 1), "unit": "images/s", "ms_per_step": round(ms_e2e / args.steps, 3),
                     "h2d_bytes_per_step": world * in_bytes, "d2h_bytes_per_step": world * out_bytes,
                     "bytes_note": "whole job (all ranks); N>1: each rank reads back its own shard, the all-gathered batch stays in HBM",
+                    "host_numa": numa,
                     "api": "llm_quest_b200.pipeline.StreamedEncoder: pinned-host fp32 pixels (+ int64 ids) in, result read back to pinned "
                            "host memory every step; upload / compute / download on 3 streams"},
             "gpu_launches": int(launches_per_step) * args.steps,
