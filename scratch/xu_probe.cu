@@ -16,6 +16,9 @@ __device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) { uint64_t d; 
 constexpr int N = 64;      // elements per thread per repetition (as one softmax step of 64 keys)
 constexpr int REP = 64;
 
+// MODE 7: MUFU + FADD2 + F2FP (no FFMA2); 8: FFMA2 + MUFU + F2FP (no FADD2); 9: softmax pattern in two phases (all FFMA2 + MUFU of
+// the 64 elements first, the row sum started from the LAST pair so that no FADD2 can be hoisted, then a branch on the last
+// exponential, then the packs); 10: as 3 but the sum chain starts from the last pair only (no branch)
 // MODE 0: MUFU only (N independent); 1: MUFU + F2FP per pair; 2: MUFU + PRMT per pair;
 // 3: softmax pattern with F2FP; 4: softmax pattern with PRMT; 5: F2FP only; 6: MUFU, dependent chain (latency)
 template <int MODE>
@@ -34,17 +37,37 @@ __global__ void probe(float* out, long long* cycles, float seed) {
 #pragma unroll
       for (int i = 0; i < N; ++i) x = ex2(x * 0.001f);
       s[0] = x;
+    } else if (MODE == 9 || MODE == 10) {
+      float e[N];
+#pragma unroll
+      for (int i = 0; i < N; i += 2) {
+        float x0, x1;
+        unpack2(ffma2(pack2(s[i], s[i + 1]), sc, nb), x0, x1);
+        e[i] = ex2(x0); e[i + 1] = ex2(x1);
+      }
+      if (MODE == 9) { if (e[N - 1] < 0.f) { out[threadIdx.x] = e[N - 1]; return; } }   // never taken; ends the basic block
+      uint64_t a0 = pack2(e[N - 2], e[N - 1]), a1 = pack2(e[N - 4], e[N - 3]);
+#pragma unroll
+      for (int i = 0; i < N - 4; i += 2) {
+        if (i & 2) a1 = fadd2(a1, pack2(e[i], e[i + 1])); else a0 = fadd2(a0, pack2(e[i], e[i + 1]));
+      }
+      acc0 = fadd2(acc0, a0); acc1 = fadd2(acc1, a1);
+#pragma unroll
+      for (int i = 0; i < N; i += 2) {
+        pk ^= f2fp(e[i], e[i + 1]);
+        s[i] = __uint_as_float(__float_as_uint(s[i]) ^ (pk & 1u)); s[i + 1] = __uint_as_float(__float_as_uint(s[i + 1]) ^ (pk & 1u));
+      }
     } else {
 #pragma unroll
       for (int i = 0; i < N; i += 2) {
         float x0 = s[i], x1 = s[i + 1];
-        if (MODE == 3 || MODE == 4) unpack2(ffma2(pack2(x0, x1), sc, nb), x0, x1);
+        if (MODE == 3 || MODE == 4 || MODE == 8) unpack2(ffma2(pack2(x0, x1), sc, nb), x0, x1);
         float p0 = x0, p1 = x1;
         if (MODE != 5) { p0 = ex2(x0); p1 = ex2(x1); }
-        if (MODE == 3 || MODE == 4) {
+        if (MODE == 3 || MODE == 4 || MODE == 7) {
           if (i & 2) acc1 = fadd2(acc1, pack2(p0, p1)); else acc0 = fadd2(acc0, pack2(p0, p1));
         }
-        if (MODE == 1 || MODE == 3 || MODE == 5) pk ^= f2fp(p0, p1);
+        if (MODE == 1 || MODE == 3 || MODE == 5 || MODE == 7 || MODE == 8) pk ^= f2fp(p0, p1);
         if (MODE == 2 || MODE == 4) pk ^= prmt(p0, p1);
         if (MODE == 0) { s[i] = p0 * 0.5f; s[i + 1] = p1 * 0.5f; }
         else { s[i] = __uint_as_float(__float_as_uint(x0) ^ (pk & 1u)); s[i + 1] = __uint_as_float(__float_as_uint(x1) ^ (pk & 1u)); }   // keep every repetition live
@@ -82,5 +105,9 @@ int main() {
   run<3>("softmax pattern: FFMA2, 2 MUFU, FADD2, F2FP", 2, out, cyc);
   run<4>("softmax pattern: FFMA2, 2 MUFU, FADD2, PRMT", 2, out, cyc);
   run<6>("MUFU.EX2 dependent chain (latency)", 2, out, cyc);
+  run<7>("2 MUFU, FADD2, F2FP (no FFMA2)", 2, out, cyc);
+  run<8>("FFMA2, 2 MUFU, F2FP (no FADD2)", 2, out, cyc);
+  run<9>("two-phase softmax pattern, branch between", 2, out, cyc);
+  run<10>("two-phase softmax pattern, sum from the last pair", 2, out, cyc);
   return 0;
 }
