@@ -83,7 +83,8 @@ struct AttnSmem {
   static constexpr int Q_OFF = 0;                               // 2 buffers x NQ tiles (next item's Q loads early)
   static constexpr int K_OFF = 2 * NQ * Q_TILE_BYTES;
   static constexpr int V_OFF = K_OFF + KV_STAGES * KV_TILE_BYTES;
-  static constexpr int BAR_OFF = V_OFF + KV_STAGES * KV_TILE_BYTES;
+  static constexpr int O_OFF = V_OFF + KV_STAGES * KV_TILE_BYTES;   // one 32-row x 32-column bf16 staging slot per softmax warp
+  static constexpr int BAR_OFF = O_OFF + NQ * 4 * 2048;
   static constexpr int TOTAL = BAR_OFF + 512 + 1024;
 };
 
@@ -163,7 +164,7 @@ __device__ __forceinline__ int pair_bh(const AttnParams& p, int item, int m) {
 template <int FLAGS>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attention_kernel(const AttnParams p, const __grid_constant__ CUtensorMap tmQ,
-                 const __grid_constant__ CUtensorMap tmKV) {
+                 const __grid_constant__ CUtensorMap tmKV, const __grid_constant__ CUtensorMap tmO) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AttnSmem::BAR_OFF);
@@ -185,6 +186,7 @@ attention_kernel(const AttnParams p, const __grid_constant__ CUtensorMap tmQ,
   if (warp == LOADER_WARP && lane == 0) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmKV);
+    tma_prefetch_desc(&tmO);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&q_full[i], 1);
       mbar_init(&q_empty[i], NQ);   // every tile walker
@@ -373,7 +375,9 @@ attention_kernel(const AttnParams p, const __grid_constant__ CUtensorMap tmQ,
             if (!mbar_try_wait(&q_full[w.qbuf], (w.qph >> w.qbuf) & 1)) return false;
             if (!mbar_try_wait(&k_full[w.ks], w.kph)) return false;
             tc_fence_after();
+            att_trace<FLAGS>(p, 16 + t, w.gstep, 2);
             if (mine) issue_s_q(t, w.ks, w.qbuf);
+            att_trace<FLAGS>(p, 16 + t, w.gstep, 3);
             commit(&k_empty[w.ks]);
             if (p.n_kt == 1) commit(&q_empty[w.qbuf]);
             if (++w.ks == w.base + w.depth) { w.ks = w.base; w.kph ^= 1; }
@@ -460,7 +464,6 @@ attention_kernel(const AttnParams p, const __grid_constant__ CUtensorMap tmQ,
         tile_row0 = qb * (128 * NQ) + t * 128;
         if (tile_row0 >= p.S) continue;                // whole tile out of range (uniform per warp)
       }
-      const int q_in_sample = tile_row0 + r_local;
 
       float m = -INFINITY;   // running (possibly stale) row max, raw score units
       float l = 0.f;         // running row sum
@@ -546,36 +549,53 @@ attention_kernel(const AttnParams p, const __grid_constant__ CUtensorMap tmQ,
         ++gstep;
       }
 
-      // ---- item epilogue: O_t / l -> global
+      // ---- item epilogue: O_t / l -> global. Every thread owns one row of 64 bf16 (128 bytes, rows 1536 bytes apart): written
+      // straight from registers that is 8 x 32 scattered 16-byte stores per warp, and the 16 warps of a CTA finish their items
+      // together — ~4000 cycles of load/store-unit time per item (a third of a key step per step at S = 784). Instead each warp
+      // stages its 32 rows x 32 columns in shared memory (64-byte swizzle) and one TMA store writes them as full lines; the
+      // output map is 3-D (column, row in sample, sample) so that rows past the end of the sample are clipped, not written
+      // into the next sample.
       att_wait(&o_full[t], oph); oph ^= 1;
       tc_fence_after();
+      att_trace<FLAGS>(p, warp, gstep - 1, 6);
       const float inv = 1.0f / l;
-      const bool row_ok = q_in_sample < p.S;
-      __nv_bfloat16* orow = p.out + (static_cast<long long>(b) * p.S + q_in_sample) * (p.H * 64) + h * 64;
+      const bool warp_ok = tile_row0 + quarter * 32 < p.S;   // at least one row of this warp exists
+      uint8_t* stage = smem + AttnSmem::O_OFF + warp * 2048;
+      const uint32_t srow = smem_u32(stage) + lane * 64;
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         uint32_t o[32];
         tmem_ld_x32(o_addr + c * 32, o);
         tmem_ld_wait();
-        if (row_ok) {
+        if (warp_ok) {
+          if (lane == 0) tma_store_wait_read<0>();   // the previous store out of this slot has left shared memory
+          __syncwarp();
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            uint4 v;
-            v.x = pack_bf16(__uint_as_float(o[q * 8 + 0]) * inv, __uint_as_float(o[q * 8 + 1]) * inv);
-            v.y = pack_bf16(__uint_as_float(o[q * 8 + 2]) * inv, __uint_as_float(o[q * 8 + 3]) * inv);
-            v.z = pack_bf16(__uint_as_float(o[q * 8 + 4]) * inv, __uint_as_float(o[q * 8 + 5]) * inv);
-            v.w = pack_bf16(__uint_as_float(o[q * 8 + 6]) * inv, __uint_as_float(o[q * 8 + 7]) * inv);
-            reinterpret_cast<uint4*>(orow + c * 32)[q] = v;
+            const uint32_t w0 = pack_bf16(__uint_as_float(o[q * 8 + 0]) * inv, __uint_as_float(o[q * 8 + 1]) * inv);
+            const uint32_t w1 = pack_bf16(__uint_as_float(o[q * 8 + 2]) * inv, __uint_as_float(o[q * 8 + 3]) * inv);
+            const uint32_t w2 = pack_bf16(__uint_as_float(o[q * 8 + 4]) * inv, __uint_as_float(o[q * 8 + 5]) * inv);
+            const uint32_t w3 = pack_bf16(__uint_as_float(o[q * 8 + 6]) * inv, __uint_as_float(o[q * 8 + 7]) * inv);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + ((q ^ ((lane >> 1) & 3)) << 4)), "r"(w0), "r"(w1),
+                         "r"(w2), "r"(w3)
+                         : "memory");
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_3d(&tmO, stage, h * 64 + c * 32, tile_row0 + quarter * 32, b);
+            tma_store_commit();
           }
         }
-        __syncwarp();
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&o_empty[t]);
+      att_trace<FLAGS>(p, warp, gstep - 1, 7);
     }
   }
 
+  if (warp < NQ * 4 && lane == 0) tma_store_wait<0>();   // shared memory must outlive the last output stores
   tc_fence_before();
   __syncthreads();
   if (warp == MMA_WARP) {
@@ -621,7 +641,7 @@ extern "C" int vf_attention_fwd(const void* qkv, void* out, int32_t B, int32_t S
   if (p.pair) p.n_items = (p.n_bh + 1) / 2;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
-  CUtensorMap tmQ, tmKV;
+  CUtensorMap tmQ, tmKV, tmO;
   uint64_t dims[2] = {(uint64_t)3 * H * 64, (uint64_t)B * S};
   uint64_t strides[1] = {(uint64_t)3 * H * 64 * 2};
   uint32_t boxq[2] = {64, 128};
@@ -631,6 +651,13 @@ extern "C" int vf_attention_fwd(const void* qkv, void* out, int32_t B, int32_t S
   e = encode_tmap(&tmKV, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, qkv, dims, strides, boxkv, CU_TENSOR_MAP_SWIZZLE_128B);
   if (e) return e;
 
+  {
+    uint64_t od[3] = {(uint64_t)H * 64, (uint64_t)S, (uint64_t)B};
+    uint64_t os[2] = {(uint64_t)H * 64 * 2, (uint64_t)S * H * 64 * 2};
+    uint32_t ob[3] = {32, 32, 1};
+    e = encode_tmap(&tmO, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, out, od, os, ob, CU_TENSOR_MAP_SWIZZLE_64B);
+    if (e) return e;
+  }
   // VF_ATTN_FLAGS=2 selects the trace build (see vf_attention_set_trace)
   static int flags = -1;
   if (flags < 0) {
@@ -640,13 +667,13 @@ extern "C" int vf_attention_fwd(const void* qkv, void* out, int32_t B, int32_t S
   p.trace = g_trace_buf;
   p.trace_first = g_trace_first;
   p.trace_n = g_trace_n;
-  using kern_t = void (*)(const AttnParams, const CUtensorMap, const CUtensorMap);
+  using kern_t = void (*)(const AttnParams, const CUtensorMap, const CUtensorMap, const CUtensorMap);
   static const kern_t kerns[2] = {attention_kernel<0>, attention_kernel<ATT_TRACE>};
   static std::atomic<uint64_t> configured[2];
   if (int e2 = ensure_dynamic_smem(kerns[flags], AttnSmem::TOTAL, configured[flags])) return e2;
   const int grid = p.n_items < sms ? p.n_items : sms;
   VF_CUDA(launch_pdl(kerns[flags], dim3(grid), dim3(ATT_THREADS), AttnSmem::TOTAL, static_cast<cudaStream_t>(stream), 1, p,
-                     tmQ, tmKV));
+                     tmQ, tmKV, tmO));
   count_launch();
   VF_CUDA(cudaGetLastError());
   return VF_OK;

@@ -39,7 +39,8 @@ for w in warps:
         d = (r[1] - r[0], r[2] - r[1], r[3] - r[2], r[4] - r[3], r[5] - r[4], per)
         if per:
             tot.setdefault(w, []).append(d)
-        print(f"w{w:02d} step {first + i:4d}: start {r[0] - t0:8d} | waitS {d[0]:5d}  ld {d[1]:4d}  max {d[2]:4d}  exp {d[3]:5d}  arrive {d[4]:4d} | period {per:5d}")
+        epi = f"  | item end: o_full +{r[6] - r[5]:5d}  O store +{r[7] - r[6]:5d}" if r[6] else ""
+        print(f"w{w:02d} step {first + i:4d}: start {r[0] - t0:8d} | waitS {d[0]:5d}  ld {d[1]:4d}  max {d[2]:4d}  exp {d[3]:5d}  arrive {d[4]:4d} | period {per:5d}{epi}")
 for w, ds in tot.items():
     m = [sum(x[k] for x in ds) / len(ds) for k in range(6)]
     print(f"# w{w:02d} mean: waitS {m[0]:.0f} ld {m[1]:.0f} max {m[2]:.0f} exp {m[3]:.0f} arrive {m[4]:.0f} period {m[5]:.0f}")
@@ -49,4 +50,5 @@ for c in range(4):
         r = [int(v) for v in t[16 + c, i]]
         if r[0] == 0:
             continue
-        print(f"mma c{c} step {first + i:4d}: at {r[0] - t0:8d} issue {r[1] - r[0]:4d}")
+        s0 = f"  | S(0) of the item issued at {r[2] - t0:8d} (+{r[3] - r[2]})" if r[2] else ""
+        print(f"mma c{c} step {first + i:4d}: at {r[0] - t0:8d} issue {r[1] - r[0]:4d}{s0}")
