@@ -445,7 +445,6 @@ attention_kernel(const AttnParams p, const __grid_constant__ CUtensorMap tmQ,
     const uint32_t lane_sel = static_cast<uint32_t>(quarter * 32) << 16;
     const uint32_t s_addr = tmem_base + lane_sel + t * 64;
     const uint32_t o_addr = tmem_base + lane_sel + 256 + t * 64;
-    const int r_local = quarter * 32 + lane;
     uint32_t sph = 0, oph = 0;
     int gstep = 0;   // key steps done by this warp (trace index)
 
