@@ -18,12 +18,12 @@ out = torch.empty(B * S, H * 64, device="cuda", dtype=torch.bfloat16)
 for _ in range(2):
     L.attention(qkv, out, B, S, H, 0.125)
 torch.cuda.synchronize()
-buf = torch.zeros(21 * n * 8, dtype=torch.int64, device="cuda")
+buf = torch.zeros(20 * n * 8, dtype=torch.int64, device="cuda")
 L.lib().vf_attention_set_trace(buf.data_ptr(), first, n)
 L.attention(qkv, out, B, S, H, 0.125)
 torch.cuda.synchronize()
 L.lib().vf_attention_set_trace(None, 0, 0)
-t = buf.cpu().view(21, n, 8)
+t = buf.cpu().view(20, n, 8)
 t0 = int(t[t > 0].min())
 print(f"# trace B={B} S={S} H={H} steps [{first},{first + n}) of block 0; cycles")
 print("# softmax warp w: start(rel) | wait_S  tmem_ld  max  exp+st_issue  st_wait+arrive | period")
@@ -50,10 +50,5 @@ for c in range(4):
         r = [int(v) for v in t[16 + c, i]]
         if r[0] == 0:
             continue
-        s0 = f"  | item picked at {r[4] - t0:8d}, first probe at {r[6] - t0:8d} ({r[7]} probes), Q there at {r[5] - t0:8d}, S(0) issued at {r[2] - t0:8d} (+{r[3] - r[2]})" if r[2] else ""
+        s0 = f"  | S(0) of the item issued at {r[2] - t0:8d} (+{r[3] - r[2]})" if r[2] else ""
         print(f"mma c{c} step {first + i:4d}: at {r[0] - t0:8d} issue {r[1] - r[0]:4d}{s0}")
-print("# loader: reaches the item whose first key step is `step` at(rel), Q buffer free +")
-for i in range(n):
-    r = [int(v) for v in t[20, i]]
-    if r[0]:
-        print(f"loader item at step {first + i:4d}: at {r[0] - t0:8d}  q_empty +{r[1] - r[0]}")
