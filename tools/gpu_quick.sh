@@ -1,12 +1,15 @@
 #!/usr/bin/env bash
-set -x
+# GPU tests + the bench line of a few configurations (cfg2 by default)
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 O=gpurun_out/quick; mkdir -p $O
-for st in 20 60; do
-timeout 300 python bench.py --steps $st --warmup 5 --no-cpu --no-eager > $O/s$st.json 2> $O/s$st.err
-python - $st <<'PY'
+timeout 900 python -m pytest tests -m gpu -q -x > $O/pytest.log 2>&1; tail -3 $O/pytest.log
+for wl in ${@:-cfg2}; do
+  f=$O/$(echo $wl | tr ':' '_')
+  timeout 600 python bench.py --workload $wl --steps 20 --warmup 5 --no-cpu > $f.json 2> $f.err
+  python - "$f.json" <<'PY'
 import json,sys
-d=json.loads(open(f'gpurun_out/quick/s{sys.argv[1]}.json').read().strip().splitlines()[-1])
-print("steps", sys.argv[1], {k:d.get(k) for k in ("value","ms_per_step","kernel_time_share_of_step")}, "e2e", d["e2e"]["ms_per_step"], d["clocks"], d["roofline"]["achieved"], d["roofline"]["frac"], d["roofline"]["peak_regime"])
+d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
+k=d.get("kernels",{})
+print(d["config"]["workload"][:40], "value",round(d["value"],1),"ms",round(d["ms_per_step"],3),"e2e",round(d["e2e"]["value"],1),"eager",(d.get("gpu_eager_baseline") or {}).get("value"),"attn",k.get("attention",{}).get("ms_per_step"),k.get("attention",{}).get("tflops"),"clk",d["clocks"]["sm_mhz"])
 PY
 done
