@@ -371,6 +371,26 @@ def test_attention(L, B, S, H):
     check_close(out, ref, tol=8e-3, what=f"attention B{B} S{S} H{H}")
 
 
+@pytest.mark.parametrize("B,S,H", [(1, 197, 2), (3, 200, 1), (2, 300, 2), (1, 530, 1)])
+def test_attention_output_store_is_clipped_at_the_sample_end(L, B, S, H):
+    """The output goes out as 32-row TMA boxes: rows past the end of a sample must be clipped by the 3-D output map, not
+    written into the next sample (checked by making the FIRST rows of every sample the only rows that could be hit and
+    comparing them bit for bit with a run where each sample is computed alone) nor past the end of the buffer (guard rows)."""
+    qkv = bf(rnd(B * S, 3 * H * 64, seed=77 + S))
+    guard = 64
+    buf = torch.full((B * S + guard, H * 64), 7.0, dtype=torch.bfloat16, device="cuda")
+    out = buf[:B * S]
+    d = dev(qkv)
+    L.attention(d, out, B, S, H, 1 / 8)
+    torch.cuda.synchronize()
+    assert bool((buf[B * S:] == 7.0).all()), "rows behind the last sample were written"
+    for b in range(B):
+        alone = torch.full((S + guard, H * 64), 7.0, dtype=torch.bfloat16, device="cuda")
+        L.attention(d[b * S:(b + 1) * S].contiguous(), alone[:S], 1, S, H, 1 / 8)
+        assert torch.equal(alone[:S], out[b * S:(b + 1) * S]), f"sample {b} differs from the same sample computed alone"
+        assert bool((alone[S:] == 7.0).all())
+
+
 def test_attention_large_scores_trigger_lazy_rescale(L):
     """Rows whose max grows tile after tile exercise the in-TMEM O rescale."""
     B, S, H = 1, 640, 1
