@@ -58,7 +58,8 @@ struct GqaSmem {
   static constexpr int Q_OFF = 0;
   static constexpr int K_OFF = GQ_BYTES;
   static constexpr int V_OFF = K_OFF + G_STAGES * GKV_BYTES;
-  static constexpr int BAR_OFF = V_OFF + G_STAGES * GKV_BYTES;
+  static constexpr int E_OFF = V_OFF + G_STAGES * GKV_BYTES;   // epilogue staging: per softmax warp a gate tile and an
+  static constexpr int BAR_OFF = E_OFF + 4 * 8192;              // output tile of 32 rows x 64 columns bf16 (4 KB each)
   static constexpr int TOTAL = BAR_OFF + 256 + 1024;
 };
 
@@ -107,7 +108,8 @@ struct GqaIter {   // same boustrophedon walk as vf_attention.cu
 
 __global__ void __launch_bounds__(G_THREADS, 1)
 attention_gqa_kernel(const GqaParams p, const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                     const __grid_constant__ CUtensorMap tmV) {
+                     const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO,
+                     const __grid_constant__ CUtensorMap tmG) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + GqaSmem::BAR_OFF);
@@ -122,7 +124,8 @@ attention_gqa_kernel(const GqaParams p, const __grid_constant__ CUtensorMap tmQ,
   uint64_t* pv_done = p_full + 2;          // [2] per S/P buffer: PV that read P from it has retired
   uint64_t* o_full = pv_done + 2;          // [1]
   uint64_t* o_empty = o_full + 1;          // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_empty + 1);
+  uint64_t* g_full = o_empty + 1;          // [4] per softmax warp: its gate tile has landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(g_full + 4);
   const char* const WHO = "vf_attention_gqa";
 
   const int warp = threadIdx.x >> 5;
@@ -148,6 +151,9 @@ attention_gqa_kernel(const GqaParams p, const __grid_constant__ CUtensorMap tmQ,
     mbar_init(&pv_done[1], 1);
     mbar_init(o_full, 1);
     mbar_init(o_empty, 4);
+    for (int i = 0; i < 4; ++i) mbar_init(&g_full[i], 1);
+    tma_prefetch_desc(&tmO);
+    if (p.gate) tma_prefetch_desc(&tmG);
     fence_barrier_init();
   }
   if (warp == 5) tmem_alloc<512>(tmem_slot);
@@ -277,17 +283,23 @@ attention_gqa_kernel(const GqaParams p, const __grid_constant__ CUtensorMap tmQ,
     const uint32_t lane_sel = static_cast<uint32_t>(warp * 32) << 16;
     const uint32_t o_addr = tmem_base + lane_sel + GT_O;
     unsigned g = 0;
-    uint32_t oph = 0;
+    uint32_t oph = 0, gph = 0;
+    uint8_t* gslot = smem + GqaSmem::E_OFF + warp * 8192;     // gate tile in, [32 rows][64 columns] bf16, 128-byte swizzle
+    uint8_t* oslot = gslot + 4096;                            // output tile out, same shape
+    const uint32_t grow = smem_u32(gslot) + lane * 128, orow = smem_u32(oslot) + lane * 128;
     int item;
     for (GqaIter it(p.n_items); it.next(item);) {
       const GqaItem w = gqa_decode(p, item);
       const int q_pos = w.qt * 128 + warp * 32 + lane;        // position of my row inside the sample
       float m = -INFINITY, l = 0.f;
-      if (p.gate && q_pos < p.S) {   // the epilogue's gate row (512 B) is pulled into L2 while the item runs
-        const char* gp = reinterpret_cast<const char*>(p.gate + (static_cast<long long>(w.b) * p.S + q_pos) * p.ldg +
-                                                       p.gate_col0 + w.h * p.gate_head_stride);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) asm volatile("prefetch.global.L2 [%0];" ::"l"(gp + i * 128));
+      // The epilogue moves 32 rows x 64 columns at a time through shared memory: gate tiles come in and output tiles go out as
+      // TMA boxes (full 128-byte lines; a row per thread straight from / to global memory costs 32 lines per warp instruction,
+      // 48 such instructions per row). The first gate tile is requested now, the others while their predecessor is in use.
+      const bool warp_ok = w.qt * 128 + warp * 32 < p.S;       // at least one row of this warp exists
+      const int g_col = p.gate_col0 + w.h * p.gate_head_stride;
+      if (p.gate && warp_ok && lane == 0) {
+        mbar_expect_tx(&g_full[warp], 4096);
+        tma_load_3d(gslot, &tmG, &g_full[warp], g_col, w.qt * 128 + warp * 32, w.b);
       }
       for (int j = 0; j < w.n_kt; ++j, ++g) {
         const uint32_t s_addr = tmem_base + lane_sel + GT_S + (g & 1) * 64;
@@ -361,46 +373,54 @@ attention_gqa_kernel(const GqaParams p, const __grid_constant__ CUtensorMap tmQ,
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[g & 1]);
       }
-      // ---- item epilogue: O / l (* sigmoid(gate)) -> global, 32 columns at a time
+      // ---- item epilogue: O / l (* sigmoid(gate)) -> global, 64 columns at a time
       mbar_wait_or_trap(o_full, oph, WHO); oph ^= 1;
       tc_fence_after();
       const float inv = 1.0f / l;
-      const bool row_ok = q_pos < p.S;
-      const long long row = static_cast<long long>(w.b) * p.S + q_pos;
-      __nv_bfloat16* orow = p.out + row * p.ldo + w.h * GD;
-      const __nv_bfloat16* grow_ = p.gate ? p.gate + row * p.ldg + p.gate_col0 + w.h * p.gate_head_stride : nullptr;
+      if (warp_ok) {
 #pragma unroll 1
-      for (int half = 0; half < 2; ++half) {     // 128 columns at a time: the row's gate values are requested together
-        uint4 gq[16];
-        if (grow_ && row_ok) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) gq[i] = __ldg(reinterpret_cast<const uint4*>(grow_ + half * 128) + i);
-        }
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint32_t o[32];
-          tmem_ld_x32(o_addr + half * 128 + c * 32, o);
+        for (int c = 0; c < GD / 64; ++c) {
+          uint32_t o[64];
+          tmem_ld_x32(o_addr + c * 64, o);
+          tmem_ld_x32(o_addr + c * 64 + 32, o + 32);
           tmem_ld_wait();
-          if (row_ok) {
+          uint32_t pk[32];
+          if (p.gate) {
+            mbar_wait_or_trap(&g_full[warp], gph, WHO); gph ^= 1;
+            uint32_t gq[32];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              float v[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(o[q * 8 + e]) * inv;
-              if (grow_) {
-                const uint4 g4 = gq[c * 4 + q];
-                const uint32_t gw[4] = {g4.x, g4.y, g4.z, g4.w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {   // sigmoid(x) = 0.5 tanh(x/2) + 0.5: one MUFU op per element
-                  v[2 * e] *= fmaf(0.5f, fast_tanh(0.5f * bf16_lo(gw[e])), 0.5f);
-                  v[2 * e + 1] *= fmaf(0.5f, fast_tanh(0.5f * bf16_hi(gw[e])), 0.5f);
-                }
-              }
-              reinterpret_cast<uint4*>(orow + half * 128 + c * 32)[q] =
-                  make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+            for (int k = 0; k < 8; ++k)
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                           : "=r"(gq[4 * k]), "=r"(gq[4 * k + 1]), "=r"(gq[4 * k + 2]), "=r"(gq[4 * k + 3])
+                           : "r"(grow + ((k ^ (lane & 7)) << 4)));
+            __syncwarp();                        // every lane has its gate values: the tile may be overwritten
+            if (lane == 0 && c + 1 < GD / 64) {
+              mbar_expect_tx(&g_full[warp], 4096);
+              tma_load_3d(gslot, &tmG, &g_full[warp], g_col + (c + 1) * 64, w.qt * 128 + warp * 32, w.b);
             }
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {       // sigmoid(x) = 0.5 tanh(x/2) + 0.5: one MUFU op per element
+              const float v0 = __uint_as_float(o[2 * e]) * inv * fmaf(0.5f, fast_tanh(0.5f * bf16_lo(gq[e])), 0.5f);
+              const float v1 = __uint_as_float(o[2 * e + 1]) * inv * fmaf(0.5f, fast_tanh(0.5f * bf16_hi(gq[e])), 0.5f);
+              pk[e] = pack_bf16(v0, v1);
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) pk[e] = pack_bf16(__uint_as_float(o[2 * e]) * inv, __uint_as_float(o[2 * e + 1]) * inv);
           }
+          if (lane == 0) tma_store_wait_read<0>();   // the previous store out of the output tile has left shared memory
           __syncwarp();
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(orow + ((k ^ (lane & 7)) << 4)), "r"(pk[4 * k]),
+                         "r"(pk[4 * k + 1]), "r"(pk[4 * k + 2]), "r"(pk[4 * k + 3])
+                         : "memory");
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_3d(&tmO, oslot, w.h * GD + c * 64, w.qt * 128 + warp * 32, w.b);
+            tma_store_commit();
+          }
         }
       }
       tc_fence_before();
@@ -409,6 +429,7 @@ attention_gqa_kernel(const GqaParams p, const __grid_constant__ CUtensorMap tmQ,
     }
   }
 
+  if (warp < 4 && lane == 0) tma_store_wait<0>();   // shared memory must outlive the last output stores
   tc_fence_before();
   __syncthreads();
   if (warp == 5) {
@@ -477,12 +498,29 @@ extern "C" int vf_attention_gqa_fwd(const void* q, int64_t ldq, int32_t q_col0, 
     int e = encode_tmap(&tmV, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, v, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
     if (e) return e;
   }
+  CUtensorMap tmO, tmG;
+  {   // 3-D (column, row in sample, sample): boxes that run past the end of a sample are clipped / zero-filled
+    uint64_t dims[3] = {(uint64_t)Hq * GD, (uint64_t)S, (uint64_t)B};
+    uint64_t strides[2] = {(uint64_t)ldo * 2, (uint64_t)S * ldo * 2};
+    uint32_t box[3] = {64, 32, 1};
+    int e = encode_tmap(&tmO, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, out, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (e) return e;
+    tmG = tmO;
+    if (gate) {
+      VF_REQUIRE(gate_col0 + (long long)(Hq - 1) * gate_head_stride + GD <= ldg, VF_ERR_ARG,
+                 "vf_attention_gqa_fwd: gate heads do not fit the row pitch");
+      uint64_t gd[3] = {(uint64_t)gate_col0 + (uint64_t)(Hq - 1) * gate_head_stride + GD, (uint64_t)S, (uint64_t)B};
+      uint64_t gs[2] = {(uint64_t)ldg * 2, (uint64_t)S * ldg * 2};
+      e = encode_tmap(&tmG, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, gate, gd, gs, box, CU_TENSOR_MAP_SWIZZLE_128B);
+      if (e) return e;
+    }
+  }
   const int sms = device_sm_count();
   VF_REQUIRE(sms > 0, VF_ERR_NO_DEVICE, "no CUDA device");
   const int grid = p.n_items < sms ? p.n_items : sms;
   static std::atomic<uint64_t> configured{0};
   if (int e2 = ensure_dynamic_smem(attention_gqa_kernel, GqaSmem::TOTAL, configured)) return e2;
-  attention_gqa_kernel<<<grid, G_THREADS, GqaSmem::TOTAL, static_cast<cudaStream_t>(stream)>>>(p, tmQ, tmK, tmV);
+  attention_gqa_kernel<<<grid, G_THREADS, GqaSmem::TOTAL, static_cast<cudaStream_t>(stream)>>>(p, tmQ, tmK, tmV, tmO, tmG);
   count_launch();
   VF_CUDA(cudaGetLastError());
   return VF_OK;

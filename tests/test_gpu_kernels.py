@@ -618,6 +618,28 @@ def test_attention_gqa(L, B, S, Hq, Hkv, causal, gate):
     check_close(out, ref.reshape(B * S, Hq * 256), tol=6e-3, what=f"gqa attention B{B} S{S} Hq{Hq}/{Hkv} causal={causal} gate={gate}")
 
 
+@pytest.mark.parametrize("B,S", [(1, 100), (3, 161), (2, 300)])
+def test_attention_gqa_output_store_is_clipped_at_the_sample_end(L, B, S):
+    """Output tiles leave as 32-row TMA boxes and gate tiles arrive the same way: rows past a sample's end must neither be
+    written (guard rows; every sample equal to the same sample computed alone) nor leak gate values of the next sample."""
+    Hq, Hkv, guard = 4, 2, 64
+    qg = dev(bf(rnd(B * S, Hq * 512, seed=61 + S)))
+    k, v = dev(bf(rnd(B * S, Hkv * 256, seed=62))), dev(bf(rnd(B * S, Hkv * 256, seed=63)))
+    buf = torch.full((B * S + guard, Hq * 256), 7.0, dtype=torch.bfloat16, device="cuda")
+    L.attention_gqa(qg, k, v, buf[:B * S], B, S, Hq, Hkv, 256 ** -0.5, True, q_col0=0, q_head_stride=512, gate2d=qg, gate_col0=256,
+                    gate_head_stride=512)
+    torch.cuda.synchronize()
+    assert bool((buf[B * S:] == 7.0).all()), "rows behind the last sample were written"
+    for b in range(B):
+        alone = torch.full((S + guard, Hq * 256), 7.0, dtype=torch.bfloat16, device="cuda")
+        sl = slice(b * S, (b + 1) * S)
+        qb = qg[sl].contiguous()
+        L.attention_gqa(qb, k[sl].contiguous(), v[sl].contiguous(), alone[:S], 1, S, Hq, Hkv, 256 ** -0.5, True, q_col0=0,
+                        q_head_stride=512, gate2d=qb, gate_col0=256, gate_head_stride=512)
+        assert torch.equal(alone[:S], buf[sl]), f"sample {b} differs from the same sample computed alone"
+        assert bool((alone[S:] == 7.0).all())
+
+
 def test_attention_gqa_large_scores_redo_path(L):
     """Scores that grow along the sequence force the runaway-sum redo (fresh max + O rescale) in later key tiles."""
     B, S, Hq, Hkv = 1, 320, 2, 1
