@@ -2,7 +2,7 @@
 """bench.py — images/sec of the vision encode (+ fuse) hot path on B200.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--device cpu|cuda]
-                    [--workload cfg1|cfg2|cfg3|cfg4|cfg5:<px>] [--no-graph] [--no-cpu] [--no-eager]
+                    [--workload cfg1|cfg2|cfg3|cfg4|cfg5:<px>] [--no-graph] [--no-cpu] [--no-eager] [--no-u8]
 
 Workloads = BASELINE.json `configs`; the default and the configuration the metric is quoted on is cfg2:
   cfg1       Part-1 ViT-B/16 classifier forward, 224x224, batch 8 per GPU, fp32 parameters
@@ -612,6 +612,51 @@ def run_ours(args):
         ms_e2e = float(t_e2e.item())
         out_bytes = enc.last_out_bytes
 
+        # Informational: the same end-to-end loop fed the way the reference's image path really starts — uint8
+        # frames (qwen3_5_generate_multimodal.py:40-46 turns one image into fp32 pixels and repeats it on the temporal axis) —
+        # with normalisation and the temporal repeat done by vf_preprocess_u8 on the device: 1/8 of the upload.
+        e2e_u8 = None
+        if isinstance(wl, TowerWorkload) and wl.T == 2 and not args.no_u8:
+            from llm_quest_b200.qwen.qwen3_5.preprocess import pixels_from_uint8
+
+            enc = None
+            g8 = torch.Generator().manual_seed(4321 + rank)
+            host_u8 = torch.randint(0, 256, (B, wl.px, wl.px, 3), dtype=torch.uint8, generator=g8).pin_memory()
+            mean, std = (0.5, 0.5, 0.5), (0.5, 0.5, 0.5)
+
+            def u8_model(frames):
+                out = model(pixels_from_uint8(frames, mean, std, 2, torch.float32), gather=fused) if fused is not None else \
+                    model(pixels_from_uint8(frames, mean, std, 2, torch.float32))
+                return out[rank * B:(rank + 1) * B] if fused is not None else out
+
+            enc8 = StreamedEncoder(u8_model, depth=2, device=dev, graph=not args.no_graph,
+                                   before_slot=(lambda i: fused.set_next_slot(1 + i)) if fused is not None else None)
+
+            def run_u8(steps):
+                for _ in range(steps):
+                    enc8.submit(host_u8)
+                    for out in enc8.ready():
+                        sink[0] += float(out[0].flatten()[0])
+                for out in enc8.drain():
+                    sink[0] += float(out[0].flatten()[0])
+
+            run_u8(3)
+            barrier()
+            e0.record()
+            run_u8(args.steps)
+            torch.cuda.synchronize()
+            e1.record()
+            barrier()
+            t8 = torch.tensor([e0.elapsed_time(e1)], device=dev)
+            if world > 1:
+                dist.all_reduce(t8, op=dist.ReduceOp.MAX)
+            e2e_u8 = {"value": round(world * wl.images() * args.steps / (float(t8.item()) / 1e3), 1), "unit": "images/s",
+                      "ms_per_step": round(float(t8.item()) / args.steps, 3), "h2d_bytes_per_step": world * host_u8.numel(),
+                      "d2h_bytes_per_step": world * enc8.last_out_bytes,
+                      "note": "informational: uint8 frames [B, H, W, 3] in, normalise + temporal repeat on the device (vf_preprocess_u8); "
+                              "same tower work per image, not the metric's input format"}
+            enc8 = None
+
     ms_step = ms_total / args.steps
     imgs = wl.images()
     value = world * imgs * args.steps / (ms_total / 1e3)
@@ -676,11 +721,13 @@ def run_ours(args):
             "launches_per_step": int(launches_per_step),
             "clocks": ck,
         }
+        if e2e_u8 is not None:
+            line["e2e_from_uint8_frames"] = e2e_u8
         if gather_check is not None:
             line["fused_gather_equals_nccl"] = gather_check
     # the baselines run on rank 0 at N = 1 only
     if rank == 0 and world == 1:
-        del enc
+        enc = None
         torch.cuda.empty_cache()
         from baseline import ref
 
@@ -714,6 +761,7 @@ def main():
     ap.add_argument("--cpu-batch", type=int, default=None, help="samples per step of the CPU baseline sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-eager", action="store_true", help="skip the gpu_eager_baseline leg")
+    ap.add_argument("--no-u8", action="store_true", help="skip the informational uint8-frames end-to-end leg")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a CUDA-graph replay")
     args = ap.parse_args()
     if args.impl == "reference":
