@@ -11,7 +11,7 @@
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("%s failed: %s\n", #x, cudaGetErrorString(e_)); exit(1); } } while (0)
 
-constexpr int STAGES = 5, STAGE_BYTES = 32768, KSTEPS = 12, NBLK = 12;
+constexpr int STAGE_BYTES = 32768, KSTEPS = 12, NBLK = 12;
 
 __device__ __forceinline__ uint32_t s32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 __device__ __forceinline__ void bar_init(uint64_t* b, int n) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s32(b)), "r"(n)); }
@@ -42,7 +42,7 @@ __device__ __forceinline__ void cluster_sync() { asm volatile("barrier.cluster.a
 // MODE 0: every CTA loads its own A and B halves (what a CTA pair does today); MODE 1: clusters of 4 = two pairs on neighbouring row
 // blocks and the same column block: every CTA loads its A half and HALF of its B half, multicast to the CTA of the other pair that
 // needs the same columns.
-template <int MODE>
+template <int MODE, int STAGES>
 __global__ void __launch_bounds__(128, 1) feed(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                                                const __grid_constant__ CUtensorMap tmBq, int steps, int m_blocks, long long* cycles) {
   extern __shared__ uint8_t raw[];
@@ -110,16 +110,12 @@ static CUtensorMap make_map(void* base, uint64_t rows, uint64_t cols, uint32_t b
   return m;
 }
 
-int main() {
-  const int M = 50176, N = 3072, K = 768, steps = KSTEPS * NBLK * 6;
-  void *A, *B; long long* cyc;
-  CK(cudaMalloc(&A, (size_t)M * K * 2)); CK(cudaMalloc(&B, (size_t)N * K * 2)); CK(cudaMalloc(&cyc, 8));
-  CK(cudaMemset(A, 0, (size_t)M * K * 2)); CK(cudaMemset(B, 0, (size_t)N * K * 2));
-  CUtensorMap tmA = make_map(A, M, K, 128), tmB = make_map(B, N, K, 128), tmBq = make_map(B, N, K, 64);
+template <int STAGES>
+void run_all(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmBq, int steps, int M, long long* cyc, cudaEvent_t e0, cudaEvent_t e1) {
   const int smem = STAGES * STAGE_BYTES + 1024 + 256;
-  CK(cudaFuncSetAttribute(feed<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  CK(cudaFuncSetAttribute(feed<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  CK(cudaFuncSetAttribute(feed<0, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  CK(cudaFuncSetAttribute(feed<1, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  printf("-- %d stages of 32 KB in flight per CTA\n", STAGES);
   for (int mode = 0; mode < 2; ++mode) {
     for (int grid : {148, 132}) {
       if (mode == 1 && grid == 148) continue;
@@ -130,8 +126,8 @@ int main() {
       float best = 1e9f; long long c = 0;
       for (int rep = 0; rep < 4; ++rep) {
         cudaEventRecord(e0);
-        if (mode == 0) CK(cudaLaunchKernelEx(&cfg, feed<0>, tmA, tmB, tmBq, steps, M / 256, cyc));
-        else CK(cudaLaunchKernelEx(&cfg, feed<1>, tmA, tmB, tmBq, steps, M / 256, cyc));
+        if (mode == 0) CK(cudaLaunchKernelEx(&cfg, feed<0, STAGES>, tmA, tmB, tmBq, steps, M / 256, cyc));
+        else CK(cudaLaunchKernelEx(&cfg, feed<1, STAGES>, tmA, tmB, tmBq, steps, M / 256, cyc));
         cudaEventRecord(e1);
         CK(cudaDeviceSynchronize());
         float ms; cudaEventElapsedTime(&ms, e0, e1);
@@ -146,5 +142,19 @@ int main() {
              100.0 * 512.0 / ((double)c / steps) * grid / 148.0);
     }
   }
+}
+
+int main() {
+  const int M = 50176, N = 3072, K = 768, steps = KSTEPS * NBLK * 6;
+  void *A, *B; long long* cyc;
+  CK(cudaMalloc(&A, (size_t)M * K * 2)); CK(cudaMalloc(&B, (size_t)N * K * 2)); CK(cudaMalloc(&cyc, 8));
+  CK(cudaMemset(A, 0, (size_t)M * K * 2)); CK(cudaMemset(B, 0, (size_t)N * K * 2));
+  CUtensorMap tmA = make_map(A, M, K, 128), tmB = make_map(B, N, K, 128), tmBq = make_map(B, N, K, 64);
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  run_all<2>(tmA, tmB, tmBq, steps, M, cyc, e0, e1);
+  run_all<3>(tmA, tmB, tmBq, steps, M, cyc, e0, e1);
+  run_all<5>(tmA, tmB, tmBq, steps, M, cyc, e0, e1);
+  run_all<6>(tmA, tmB, tmBq, steps, M, cyc, e0, e1);
   return 0;
 }
+
