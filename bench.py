@@ -721,6 +721,11 @@ def run_ours(args):
             "launches_per_step": int(launches_per_step),
             "clocks": ck,
         }
+        if isinstance(wl, TowerWorkload):
+            # a video sample counts as one sample and also as its T raw frames — report both next to the
+            # image-equivalents (T/2 temporal patches) `value` is quoted in
+            sps = world * B * args.steps / (ms_total / 1e3)
+            line["samples_per_s"], line["raw_frames_per_s"] = round(sps, 1), round(sps * wl.T, 1)
         if e2e_u8 is not None:
             line["e2e_from_uint8_frames"] = e2e_u8
         if gather_check is not None:
