@@ -391,6 +391,18 @@ def test_attention_output_store_is_clipped_at_the_sample_end(L, B, S, H):
         assert bool((alone[S:] == 7.0).all())
 
 
+@pytest.mark.parametrize("B,S,H", [(80, 196, 2), (151, 197, 1), (50, 100, 3), (75, 256, 2)])
+def test_attention_pair_mode(L, B, S, H):
+    """S <= 256 with more (sample, head) pairs than SMs: a work item is a PAIR of (sample, head) (chains 0,1 / 2,3, two K/V
+    rings); 151 x 1 leaves the last item without a second member, S = 100 gives one query tile per member."""
+    qkv = bf(rnd(B * S, 3 * H * 64, seed=90 + S))
+    out = torch.full((B * S, H * 64), float("nan"), dtype=torch.bfloat16, device="cuda")
+    L.attention(dev(qkv), out, B, S, H, 1 / 8)
+    q, k, v = (qkv.float().view(B, S, 3, H, 64)[:, :, i].transpose(1, 2) for i in range(3))
+    ref = (torch.softmax(q @ k.transpose(-1, -2) / 8, -1) @ v).transpose(1, 2).reshape(B * S, H * 64)
+    check_close(out, ref, tol=8e-3, what=f"attention pair mode B{B} S{S} H{H}")
+
+
 def test_attention_large_scores_trigger_lazy_rescale(L):
     """Rows whose max grows tile after tile exercise the in-TMEM O rescale."""
     B, S, H = 1, 640, 1
