@@ -39,6 +39,27 @@ def test_version_and_error_string(lib):
     assert isinstance(lib.vf_last_error(), bytes)
 
 
+def test_ctypes_struct_layout_matches_the_header(tmp_path):
+    """vf_epilogue crosses the C-ABI by pointer: the ctypes mirror in _lib.py must have the header's size and field offsets (a C
+    program that includes include/vfuse.h prints them; plain gcc, as a reference-side binding would compile it)."""
+    import subprocess
+
+    from llm_quest_b200 import _lib
+
+    names = [f[0] for f in _lib.vf_epilogue._fields_]
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stddef.h>\n#include <stdio.h>\n#include "vfuse.h"\nint main(void) {\n  printf("%zu\\n", sizeof(vf_epilogue));\n'
+                   + "".join(f'  printf("{n} %zu\\n", offsetof(vf_epilogue, {n}));\n' for n in names) + "  return 0;\n}\n")
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c11", "-Wall", "-Werror", "-I", str(ROOT / "include"), str(src), "-o", str(exe)], check=True)
+    lines = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split("\n")
+    assert int(lines[0]) == ctypes.sizeof(_lib.vf_epilogue)
+    for line in lines[1:]:
+        if line:
+            n, off = line.split()
+            assert getattr(_lib.vf_epilogue, n).offset == int(off), n
+
+
 def test_argument_validation_without_gpu(lib):
     """Pure argument checks run before any CUDA call, so they are testable on a CPU box."""
     lib.vf_last_error.restype = ctypes.c_char_p
