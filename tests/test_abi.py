@@ -60,6 +60,42 @@ def test_ctypes_struct_layout_matches_the_header(tmp_path):
             assert getattr(_lib.vf_epilogue, n).offset == int(off), n
 
 
+def test_ctypes_signatures_match_the_header_prototypes(lib):
+    """Every prototype in include/vfuse.h against the argtypes _lib.py binds: same number of parameters, and pointer / int32 / int64 /
+    float in the same positions (a swapped pair of ints would otherwise only show up as a wrong result on the GPU)."""
+    from llm_quest_b200 import _lib
+
+    L = _lib.lib()
+    header = re.sub(r"/\*.*?\*/", "", (ROOT / "include" / "vfuse.h").read_text(), flags=re.S)
+    header = re.sub(r"//[^\n]*", "", header)
+    protos = re.findall(r"\bint\s+(vf_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", header, flags=re.S)
+    assert len(protos) >= 20
+
+    def kind_c(arg):
+        if "*" in arg:
+            return "ptr"
+        for t, k in (("int64_t", "i64"), ("int32_t", "i32"), ("float", "f32"), ("int", "i32")):
+            if re.search(rf"\b{t}\b", arg):
+                return k
+        raise AssertionError(arg)
+
+    def kind_py(t):
+        if t is ctypes.c_void_p or t is ctypes.c_char_p or hasattr(t, "contents") or getattr(t, "_type_", None) is not None and not isinstance(getattr(t, "_type_"), str):
+            return "ptr"
+        return {ctypes.c_int32: "i32", ctypes.c_int64: "i64", ctypes.c_float: "f32", ctypes.c_int: "i32"}[t]
+
+    checked = 0
+    for name, args in protos:
+        fn = getattr(L, name)
+        if fn.argtypes is None:
+            continue
+        c_kinds = [kind_c(a) for a in args.split(",") if a.strip() and a.strip() != "void"]
+        py_kinds = [kind_py(t) for t in fn.argtypes]
+        assert c_kinds == py_kinds, (name, c_kinds, py_kinds)
+        checked += 1
+    assert checked >= 20
+
+
 def test_argument_validation_without_gpu(lib):
     """Pure argument checks run before any CUDA call, so they are testable on a CPU box."""
     lib.vf_last_error.restype = ctypes.c_char_p
